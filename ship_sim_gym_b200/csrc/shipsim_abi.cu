@@ -1,0 +1,412 @@
+// shipsim_abi.cu -- the C ABI of libshipsim.so (include/shipsim.h): handle management, scenario packing,
+// parameter derivation and kernel launches.  Host-side C++; no torch types anywhere.
+#include "../../include/shipsim.h"
+#include "shipsim_device.cuh"
+#include "shipsim_launch.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace shipsim;
+
+struct shipsim_handle {
+    shipsim_config cfg;
+    int device = 0;
+    StepParams p;
+    float4 *d_bank = nullptr;
+    int lanes = 1;
+    // staging for shipsim_step_host (allocated on first use, sized for the largest K seen)
+    int32_t *d_act = nullptr; float *d_obs = nullptr; float *d_rew = nullptr; uint8_t *d_done = nullptr;
+    int stage_K = 0;
+    int64_t launches = 0;
+    LaunchShape shape{1, kThreadsT1, 0};
+};
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(expr)                                                                                      \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess)                                                                        \
+            return fail(SHIPSIM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+extern "C" int shipsim_abi_version(void) { return SHIPSIM_ABI_VERSION; }
+extern "C" const char *shipsim_last_error(void) { return g_err.c_str(); }
+
+extern "C" int shipsim_config_default(shipsim_config *c)
+{
+    if (!c) return fail(SHIPSIM_ERR_ARG, "cfg is NULL");
+    std::memset(c, 0, sizeof(*c));
+    c->struct_size = (int32_t)sizeof(shipsim_config);
+    c->num_envs = 1;
+    c->bounds_w = 600.f; c->bounds_h = 600.f;                 // config.py:24
+    c->dt = 1.0f;                                             // SPEED 10 * base_dt 0.1 (config.py:23, game.py:27)
+    c->damping = (float)std::pow(0.4, 1.0);                   // game.py:270
+    c->max_steps = 1000; c->history = 2;                      // config.py:15-16
+    c->auto_reset = 1;
+    c->lidar_beams = SHIPSIM_N_BEAMS; c->lidar_spread_deg = 90.f; c->lidar_distance = 100.f;   // models.py:29
+    c->ship_w = 2.f; c->ship_h = 3.f;                         // game.py:275
+    c->mass = 5.f; c->thrust = 100.f;                         // models.py:87,107
+    c->goal_radius = 5.f; c->step_penalty = -0.01f; c->spawn_y = 25.f;   // game.py:82, ship_env.py:13, game.py:274
+    c->lanes_per_env = 0;
+    return SHIPSIM_OK;
+}
+
+// ---- small double-precision geometry helpers (host) --------------------------------------------------------
+namespace {
+struct P2 { double x, y; };
+
+// Convex hull, CCW, collinear points dropped, first vertex = min-x then min-y: what pm.Poly does to the
+// vertex list it is given (models.py:96,180 -> cpPolyShapeInit -> cpConvexHull tol 0).
+std::vector<P2> convex_hull_ccw(std::vector<P2> pts)
+{
+    std::sort(pts.begin(), pts.end(), [](const P2 &a, const P2 &b) { return a.x < b.x || (a.x == b.x && a.y < b.y); });
+    pts.erase(std::unique(pts.begin(), pts.end(), [](const P2 &a, const P2 &b) { return a.x == b.x && a.y == b.y; }), pts.end());
+    const int n = (int)pts.size();
+    if (n < 3) return pts;
+    std::vector<P2> h(2 * n);
+    int k = 0;
+    auto turn = [](const P2 &o, const P2 &a, const P2 &b) { return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x); };
+    for (int i = 0; i < n; ++i) { while (k >= 2 && turn(h[k - 2], h[k - 1], pts[i]) <= 0) --k; h[k++] = pts[i]; }
+    for (int i = n - 2, t = k + 1; i >= 0; --i) { while (k >= t && turn(h[k - 2], h[k - 1], pts[i]) <= 0) --k; h[k++] = pts[i]; }
+    h.resize(k - 1);
+    return h;
+}
+
+// cpMomentForPoly about the body origin (models.py:89)
+double moment_for_poly(double m, const std::vector<P2> &v)
+{
+    double s1 = 0, s2 = 0;
+    const int n = (int)v.size();
+    for (int i = 0; i < n; ++i) {
+        const P2 a = v[i], b = v[(i + 1) % n];
+        const double cr = b.x * a.y - b.y * a.x;
+        s1 += cr * (a.x * a.x + a.y * a.y + a.x * b.x + a.y * b.y + b.x * b.x + b.y * b.y);
+        s2 += cr;
+    }
+    return m * s1 / (6.0 * s2);
+}
+
+float round_down(double v) { float f = (float)v; return (double)f > v ? std::nextafterf(f, -INFINITY) : f; }
+float round_up(double v) { float f = (float)v; return (double)f < v ? std::nextafterf(f, INFINITY) : f; }
+}  // namespace
+
+static int derive_params(shipsim_handle *h)
+{
+    const shipsim_config &c = h->cfg;
+    StepParams &p = h->p;
+    std::memset(&p, 0, sizeof(p));
+    p.seed = c.seed; p.env_id_offset = c.env_id_offset; p.N = c.num_envs;
+    p.history = c.history; p.auto_reset = c.auto_reset; p.max_steps = c.max_steps;
+    p.W = c.bounds_w; p.H = c.bounds_h; p.dt = c.dt; p.damping = c.damping;
+    p.lidar_len = c.lidar_distance;
+    p.goal_r = c.goal_radius; p.step_penalty = c.step_penalty;
+    p.spawn_x = c.bounds_w / 2.f; p.spawn_y = c.spawn_y;
+    // ship hull: SHIP_TEMPLATE (models.py:6) scaled by (width, height), convexified like pm.Poly does
+    const double tpl[5][2] = {{0, 0}, {0, 10}, {5, 15}, {10, 10}, {10, 0}};
+    std::vector<P2> raw;
+    for (auto &t : tpl) raw.push_back({t[0] * c.ship_w, t[1] * c.ship_h});
+    const double moment = moment_for_poly(c.mass, raw);
+    std::vector<P2> hull = convex_hull_ccw(raw);
+    if ((int)hull.size() != kShipVerts || hull[0].x != 0.0 || hull[0].y != 0.0)
+        return fail(SHIPSIM_ERR_ARG, "ship_w / ship_h must be positive");
+    double l = 1e300, b = 1e300, r = -1e300, t = -1e300;
+    for (int j = 0; j < kShipVerts; ++j) {
+        const P2 a = hull[(j + kShipVerts - 1) % kShipVerts], v = hull[j];
+        const double ex = v.x - a.x, ey = v.y - a.y, ln = std::sqrt(ex * ex + ey * ey);
+        p.ship_lx[j] = (float)v.x; p.ship_ly[j] = (float)v.y;
+        p.ship_nx[j] = (float)(ey / ln); p.ship_ny[j] = (float)(-ex / ln);
+        l = std::min(l, v.x); r = std::max(r, v.x); b = std::min(b, v.y); t = std::max(t, v.y);
+    }
+    p.ship_aabb[0] = (float)l; p.ship_aabb[1] = (float)b; p.ship_aabb[2] = (float)r; p.ship_aabb[3] = (float)t;
+    p.acc_dt = (float)((double)c.thrust / c.mass * c.dt);
+    p.ang_dt = (float)((double)c.thrust / moment * c.dt);
+    // lidar fan (models.py:48-49,62)
+    const double deg = 3.14159265358979323846 / 180.0;
+    const double delta = ((double)c.lidar_spread_deg / c.lidar_beams) * deg;
+    const double start = (90.0 - (double)c.lidar_spread_deg / 2.0) * deg;
+    for (int i = 0; i < kBeams; ++i) { p.ray_c[i] = (float)std::cos(start + delta * i); p.ray_s[i] = (float)std::sin(start + delta * i); }
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_create(const shipsim_config *cfg, int device, shipsim_t **out)
+{
+    if (!cfg || !out) return fail(SHIPSIM_ERR_ARG, "cfg/out is NULL");
+    if (cfg->struct_size != (int32_t)sizeof(shipsim_config)) return fail(SHIPSIM_ERR_ARG, "shipsim_config size mismatch (ABI version?)");
+    if (cfg->num_envs < 1) return fail(SHIPSIM_ERR_ARG, "num_envs must be >= 1");
+    if (cfg->history < 1) return fail(SHIPSIM_ERR_ARG, "history_size must be greater than zero");   // ship_env.py:46-47
+    if (cfg->history > 2) return fail(SHIPSIM_ERR_UNSUPPORTED, "history > 2 is assembled by the host layer from 1-frame observations");
+    if (cfg->lidar_beams != SHIPSIM_N_BEAMS) return fail(SHIPSIM_ERR_UNSUPPORTED, "lidar_beams must be 10");
+    if (!(cfg->dt > 0.f) || !(cfg->bounds_w > 0.f) || !(cfg->bounds_h > 0.f) || !(cfg->lidar_distance > 0.f) || cfg->max_steps < 1
+        || cfg->max_steps >= (1 << 22))
+        return fail(SHIPSIM_ERR_ARG, "dt, bounds, lidar_distance must be positive and 1 <= max_steps < 2^22");
+    if (cfg->lanes_per_env != 0 && cfg->lanes_per_env != 1 && cfg->lanes_per_env != 8)
+        return fail(SHIPSIM_ERR_ARG, "lanes_per_env must be 0, 1 or 8");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SHIPSIM_ERR_CUDA, "no CUDA device: libshipsim has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(SHIPSIM_ERR_ARG, "bad device index");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(SHIPSIM_ERR_CUDA, "libshipsim is built for sm_100a (B200) only");
+    shipsim_handle *h = new shipsim_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    const int rc = derive_params(h);
+    if (rc != SHIPSIM_OK) { delete h; return rc; }
+    h->lanes = cfg->lanes_per_env ? cfg->lanes_per_env : 1;
+    *out = h;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_destroy(shipsim_t *h)
+{
+    if (!h) return SHIPSIM_OK;
+    DeviceGuard g(h->device);
+    cudaFree(h->d_bank); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
+    delete h;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const int32_t *hull_n, const double *goals_xy,
+                                      int32_t n_scen, int32_t maxv)
+{
+    if (!h || !hull_xy || !hull_n || !goals_xy) return fail(SHIPSIM_ERR_ARG, "NULL argument");
+    if (n_scen < 1 || maxv < 3) return fail(SHIPSIM_ERR_ARG, "need n_scenarios >= 1 and maxv >= 3");
+    int dev_maxv = 0;
+    for (int i = 0; i < n_scen * 2; ++i) {
+        if (hull_n[i] < 3 || hull_n[i] > maxv || hull_n[i] > SHIPSIM_MAX_HULL)
+            return fail(SHIPSIM_ERR_ARG, "hull vertex count out of range [3, min(maxv, 32)]");
+        dev_maxv = std::max(dev_maxv, (int)hull_n[i]);
+    }
+    const int stride4 = kBankHeader4 + 2 * dev_maxv * 2;
+    std::vector<float4> host((size_t)n_scen * stride4, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int s = 0; s < n_scen; ++s) {
+        float4 *rec = host.data() + (size_t)s * stride4;
+        for (int b = 0; b < 2; ++b) {
+            const double *v = hull_xy + ((size_t)s * 2 + b) * maxv * 2;
+            const int n = hull_n[s * 2 + b];
+            double l = 1e300, bo = 1e300, r = -1e300, t = -1e300, area2 = 0;
+            for (int i = 0; i < n; ++i) {
+                const double ax = v[2 * ((i + n - 1) % n)], ay = v[2 * ((i + n - 1) % n) + 1], bx = v[2 * i], by = v[2 * i + 1];
+                area2 += ax * by - ay * bx;
+                l = std::min(l, bx); r = std::max(r, bx); bo = std::min(bo, by); t = std::max(t, by);
+            }
+            if (!(area2 > 0)) return fail(SHIPSIM_ERR_ARG, "bank hulls must be convex and counter-clockwise");
+            rec[b] = make_float4(round_down(l), round_down(bo), round_up(r), round_up(t));
+            float4 *E = rec + kBankHeader4 + b * dev_maxv * 2;
+            for (int i = 0; i < dev_maxv; ++i) {
+                if (i < n) {
+                    const double ax = v[2 * ((i + n - 1) % n)], ay = v[2 * ((i + n - 1) % n) + 1], bx = v[2 * i], by = v[2 * i + 1];
+                    const double ex = bx - ax, ey = by - ay, ln = std::sqrt(ex * ex + ey * ey);
+                    if (!(ln > 0)) return fail(SHIPSIM_ERR_ARG, "degenerate hull edge");
+                    const double nx = ey / ln, ny = -ex / ln;                 // cpvrperp: outward for CCW
+                    E[2 * i] = make_float4((float)nx, (float)ny, (float)(nx * bx + ny * by), (float)(nx * ay - ny * ax));
+                    E[2 * i + 1] = make_float4((float)(nx * by - ny * bx), (float)bx, (float)by, 0.f);
+                } else {                                                      // padding: see shipsim_device.cuh
+                    E[2 * i] = make_float4(0.f, 0.f, 1.0e30f, 0.f);
+                    E[2 * i + 1] = make_float4(0.f, (float)v[0], (float)v[1], 0.f);
+                }
+            }
+        }
+        const double *g = goals_xy + (size_t)s * 10;
+        rec[2] = make_float4((float)g[0], (float)g[1], (float)g[2], (float)g[3]);
+        rec[3] = make_float4((float)g[4], (float)g[5], (float)g[6], (float)g[7]);
+        float4 g2 = make_float4((float)g[8], (float)g[9], 0.f, 0.f);
+        const int n0 = hull_n[s * 2], n1 = hull_n[s * 2 + 1];
+        std::memcpy(&g2.z, &n0, 4); std::memcpy(&g2.w, &n1, 4);
+        rec[4] = g2;
+    }
+    DeviceGuard g(h->device);
+    float4 *d = nullptr;
+    CU(cudaMalloc(&d, host.size() * sizeof(float4)));
+    cudaError_t e = cudaMemcpy(d, host.data(), host.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return fail(SHIPSIM_ERR_CUDA, cudaGetErrorString(e)); }
+    CU(cudaDeviceSynchronize());           // no launch may still be reading the old bank
+    cudaFree(h->d_bank);
+    h->d_bank = d;
+    h->p.bank = d; h->p.n_scen = n_scen; h->p.maxv = dev_maxv; h->p.scen_stride4 = stride4;
+    return SHIPSIM_OK;
+}
+
+extern "C" size_t shipsim_state_bytes(const shipsim_t *h) { return h ? (size_t)h->cfg.num_envs * kPlanes * sizeof(float4) : 0; }
+extern "C" size_t shipsim_stats_bytes(const shipsim_t *) { return (size_t)kStatSlots * kStatLen * sizeof(double); }
+
+extern "C" int shipsim_bind_state(shipsim_t *h, void *dev_state, void *dev_stats, void *stream)
+{
+    if (!h || !dev_state || !dev_stats) return fail(SHIPSIM_ERR_ARG, "NULL argument");
+    if (((uintptr_t)dev_state & 15) || ((uintptr_t)dev_stats & 7)) return fail(SHIPSIM_ERR_ARG, "state must be 16-byte aligned");
+    DeviceGuard g(h->device);
+    h->p.state = (float4 *)dev_state;
+    h->p.stats = (double *)dev_stats;
+    CU(cudaMemsetAsync(dev_stats, 0, shipsim_stats_bytes(h), (cudaStream_t)stream));
+    return SHIPSIM_OK;
+}
+
+static int ready(const shipsim_t *h)
+{
+    if (!h) return fail(SHIPSIM_ERR_ARG, "handle is NULL");
+    if (!h->p.bank) return fail(SHIPSIM_ERR_STATE, "shipsim_load_scenarios has not been called");
+    if (!h->p.state) return fail(SHIPSIM_ERR_STATE, "shipsim_bind_state has not been called");
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_reset(shipsim_t *h, const uint8_t *dev_mask, const int32_t *dev_scenario, int first, float *dev_obs, void *stream)
+{
+    const int rc = ready(h);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    CU(launch_reset(h->p, dev_mask, dev_scenario, first, (float4 *)dev_obs, (cudaStream_t)stream));
+    h->launches++;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_step(shipsim_t *h, const void *dev_actions, int action_dtype, int32_t K, float *dev_obs, float *dev_reward,
+                            uint8_t *dev_done, void *stream)
+{
+    const int rc = ready(h);
+    if (rc) return rc;
+    if (K < 1) return fail(SHIPSIM_ERR_ARG, "K must be >= 1");
+    if (action_dtype < 0 || action_dtype > 3) return fail(SHIPSIM_ERR_ARG, "bad action_dtype");
+    if (action_dtype != SHIPSIM_ACTION_RANDOM && !dev_actions) return fail(SHIPSIM_ERR_ARG, "dev_actions is NULL");
+    if ((uintptr_t)dev_obs & 15) return fail(SHIPSIM_ERR_ARG, "dev_obs must be 16-byte aligned");
+    DeviceGuard g(h->device);
+    StepParams p = h->p;
+    p.actions = dev_actions; p.action_dtype = action_dtype; p.K = K;
+    p.obs = (float4 *)dev_obs; p.reward = dev_reward; p.done = dev_done;
+    CU(launch_step(p, h->lanes, (cudaStream_t)stream, &h->shape));
+    h->p.step0 += (unsigned)K;
+    h->launches++;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int32_t K, float *host_obs, float *host_reward,
+                                 uint8_t *host_done, void *stream)
+{
+    const int rc = ready(h);
+    if (rc) return rc;
+    if (K < 1 || !host_actions) return fail(SHIPSIM_ERR_ARG, "K must be >= 1 and host_actions non-NULL");
+    DeviceGuard g(h->device);
+    const size_t n = (size_t)h->cfg.num_envs * K;
+    const size_t obs_f = n * kFrame * h->cfg.history;
+    if (K > h->stage_K) {
+        cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
+        h->d_act = nullptr; h->d_obs = nullptr; h->d_rew = nullptr; h->d_done = nullptr; h->stage_K = 0;
+        CU(cudaMalloc(&h->d_act, n * sizeof(int32_t)));
+        CU(cudaMalloc(&h->d_obs, obs_f * sizeof(float)));
+        CU(cudaMalloc(&h->d_rew, n * sizeof(float)));
+        CU(cudaMalloc(&h->d_done, n));
+        h->stage_K = K;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    CU(cudaMemcpyAsync(h->d_act, host_actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    const int rc2 = shipsim_step(h, h->d_act, SHIPSIM_ACTION_I32, K, h->d_obs, h->d_rew, h->d_done, stream);
+    if (rc2) return rc2;
+    if (host_obs) CU(cudaMemcpyAsync(host_obs, h->d_obs, obs_f * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (host_reward) CU(cudaMemcpyAsync(host_reward, h->d_rew, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (host_done) CU(cudaMemcpyAsync(host_done, h->d_done, n, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_stats_read(shipsim_t *h, double *dev_out, int clear, void *stream)
+{
+    const int rc = ready(h);
+    if (rc) return rc;
+    if (!dev_out) return fail(SHIPSIM_ERR_ARG, "dev_out is NULL");
+    DeviceGuard g(h->device);
+    CU(launch_stats_reduce(h->p.stats, dev_out, clear, (cudaStream_t)stream));
+    h->launches++;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_set_state(shipsim_t *h, const float *pose, const int32_t *ints, const float *lidar, const float *goals,
+                                 const float *ep_return)
+{
+    const int rc = ready(h);
+    if (rc) return rc;
+    if (!pose || !ints || !lidar || !goals || !ep_return) return fail(SHIPSIM_ERR_ARG, "NULL argument");
+    const size_t N = (size_t)h->cfg.num_envs;
+    std::vector<float4> st(N * kPlanes);
+    for (size_t e = 0; e < N; ++e) {
+        const float *q = pose + e * 6, *l = lidar + e * 10, *gl = goals + e * 10;
+        const int32_t *in = ints + e * 5;
+        if (in[0] % 5 != 0 || in[0] < -10 || in[0] > 10) return fail(SHIPSIM_ERR_ARG, "rudder must be in {-10,-5,0,5,10}");
+        if (in[3] < 0 || in[3] >= h->p.n_scen) return fail(SHIPSIM_ERR_ARG, "scenario id out of range");
+        const int bits = ((in[0] / 5 + 2) & 7) | ((in[1] & 31) << 3) | (in[2] << 8);
+        float fb, fs, fe;
+        std::memcpy(&fb, &bits, 4); std::memcpy(&fs, &in[3], 4); std::memcpy(&fe, &in[4], 4);
+        st[0 * N + e] = make_float4(q[0], q[1], q[2], q[3]);
+        st[1 * N + e] = make_float4(q[4], q[5], ep_return[e], fb);
+        st[2 * N + e] = make_float4(l[0], l[1], l[2], l[3]);
+        st[3 * N + e] = make_float4(l[4], l[5], l[6], l[7]);
+        st[4 * N + e] = make_float4(l[8], l[9], fs, fe);
+        st[5 * N + e] = make_float4(gl[0], gl[1], gl[2], gl[3]);
+        st[6 * N + e] = make_float4(gl[4], gl[5], gl[6], gl[7]);
+        st[7 * N + e] = make_float4(gl[8], gl[9], 0.f, 0.f);
+    }
+    DeviceGuard g(h->device);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h->p.state, st.data(), st.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_get_state(shipsim_t *h, float *pose, int32_t *ints, float *lidar, float *goals, float *ep_return)
+{
+    const int rc = ready(h);
+    if (rc) return rc;
+    const size_t N = (size_t)h->cfg.num_envs;
+    std::vector<float4> st(N * kPlanes);
+    DeviceGuard g(h->device);
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(st.data(), h->p.state, st.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (size_t e = 0; e < N; ++e) {
+        const float4 a = st[0 * N + e], b = st[1 * N + e], l0 = st[2 * N + e], l1 = st[3 * N + e], l2 = st[4 * N + e];
+        const float4 g0 = st[5 * N + e], g1 = st[6 * N + e], g2 = st[7 * N + e];
+        int bits, scen, ep;
+        std::memcpy(&bits, &b.w, 4); std::memcpy(&scen, &l2.z, 4); std::memcpy(&ep, &l2.w, 4);
+        if (pose) { float *q = pose + e * 6; q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w; q[4] = b.x; q[5] = b.y; }
+        if (ep_return) ep_return[e] = b.z;
+        if (ints) { int32_t *in = ints + e * 5; in[0] = ((bits & 7) - 2) * 5; in[1] = (bits >> 3) & 31; in[2] = bits >> 8; in[3] = scen; in[4] = ep; }
+        if (lidar) { float *l = lidar + e * 10; l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w; l[8] = l2.x; l[9] = l2.y; }
+        if (goals) { float *gl = goals + e * 10; gl[0] = g0.x; gl[1] = g0.y; gl[2] = g0.z; gl[3] = g0.w; gl[4] = g1.x; gl[5] = g1.y; gl[6] = g1.z; gl[7] = g1.w; gl[8] = g2.x; gl[9] = g2.y; }
+    }
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_launch_count(const shipsim_t *h, int64_t *out)
+{
+    if (!h || !out) return fail(SHIPSIM_ERR_ARG, "NULL argument");
+    *out = h->launches;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_launch_shape(const shipsim_t *h, int32_t *lanes, int32_t *threads, int32_t *ctas)
+{
+    if (!h) return fail(SHIPSIM_ERR_ARG, "NULL argument");
+    if (lanes) *lanes = h->shape.lanes_per_env;
+    if (threads) *threads = h->shape.threads;
+    if (ctas) *ctas = h->shape.blocks;
+    return SHIPSIM_OK;
+}

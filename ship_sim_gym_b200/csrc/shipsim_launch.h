@@ -1,0 +1,18 @@
+// shipsim_launch.h -- host-visible launch wrappers implemented in shipsim_kernels.cu
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace shipsim {
+
+struct StepParams;
+constexpr int kThreadsT1 = 128;
+
+struct LaunchShape { int lanes_per_env, threads, blocks; };
+
+cudaError_t launch_step(const StepParams &p, int lanes_per_env, cudaStream_t stream, LaunchShape *shape);
+cudaError_t launch_reset(const StepParams &p, const uint8_t *mask, const int *scenario, int first, float4 *obs,
+                         cudaStream_t stream);
+cudaError_t launch_stats_reduce(double *slots, double *out, int clear, cudaStream_t stream);
+
+}  // namespace shipsim

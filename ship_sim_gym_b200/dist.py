@@ -1,0 +1,52 @@
+"""One process per GPU.  Environments are independent units (each ShipEnv owns its own ShipGame,
+ship_env.py:32), so the batch shards into contiguous blocks of global env ids with NO data-path collective; the
+only exchange is one all-reduce(SUM) of the 16-double episode-statistics vector per rollout (NCCL over
+NVLink on GPUs, gloo in the CPU tests)."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def env_info():
+    """(rank, world_size, local_rank) from the torchrun environment (defaults: single process)."""
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+
+
+def init(backend=None):
+    """Join the process group described by RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT, if any."""
+    rank, world, local = env_info()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        kw = {}
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, **kw)
+    return rank, world, local
+
+
+def shard(total_envs, rank, world):
+    """Contiguous block [offset, offset+count) of global env ids owned by `rank` (sizes differ by at most 1)."""
+    base, rem = divmod(int(total_envs), int(world))
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+def all_reduce_stats(stats):
+    """In-place SUM over ranks of the float64[16] statistics vector; no-op in a single process."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    return stats
+
+
+def summarize(stats_vec, names):
+    """Global means from the reduced vector (what Curriculum.progress is fed)."""
+    v = [float(x) for x in stats_vec.tolist()]
+    d = dict(zip(names, v))
+    ep = max(d.get("episodes", 0.0), 1.0)
+    d["mean_return"] = d.get("return_sum", 0.0) / ep
+    d["mean_length"] = d.get("length_sum", 0.0) / ep
+    return d

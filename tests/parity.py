@@ -1,0 +1,105 @@
+"""Kernel-vs-oracle comparison helpers (used by the -m gpu tests, smoke() and bench's self-check).
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8d): pose, velocity, lidar within 1e-4 * max(1, |ref|);
+reward / done / flags bit-exact -- away from grazing configurations, which the oracle identifies through the
+margins it reports (distance of every evaluated inequality from its decision boundary, in length units).
+"""
+import numpy as np
+
+REL_TOL = 1e-4
+# margin layout of the oracle: [0] ship-bank SAT |separation|, [1] |goal distance - r|, [2] out-of-bounds slack,
+# [3] nearest-goal tie slack, [4+i] lidar ray i
+M_SAT, M_GOAL, M_OOB, M_TIE, M_RAY0 = 0, 1, 2, 3, 4
+
+
+def random_states(rng, n, W, H, n_scen, bank_goals, max_steps=1000, near=None):
+    """Injected-state distribution of SURVEY.md §8(d)."""
+    pose = np.zeros((n, 6))
+    pose[:, 0] = rng.uniform(0, W, n)
+    pose[:, 1] = rng.uniform(0, H, n)
+    pose[:, 2] = rng.uniform(-np.pi, np.pi, n)
+    pose[:, 3:5] = rng.uniform(-40, 40, (n, 2))
+    pose[:, 5] = rng.uniform(-0.3, 0.3, n)
+    ints = np.zeros((n, 5), dtype=np.int32)
+    ints[:, 0] = rng.choice([-10, -5, 0, 5, 10], n)
+    ints[:, 1] = rng.randint(0, 32, n)
+    ints[:, 2] = rng.randint(0, max_steps, n)
+    ints[:, 3] = rng.randint(0, n_scen, n)
+    ints[:, 4] = rng.randint(0, 50, n)
+    lidar = np.where(rng.rand(n, 10) < 0.5, -1.0, rng.uniform(0, 100, (n, 10)))
+    goals = bank_goals[ints[:, 3]].copy()
+    ret = rng.uniform(-3, 3, n)
+    if near is not None:        # adversarial: put the ship close to a vertex of one of its banks
+        hull_xy, hull_n = near
+        for e in range(0, n, 2):
+            s = ints[e, 3]
+            b = rng.randint(0, 2)
+            v = hull_xy[s, b, rng.randint(0, hull_n[s, b])]
+            pose[e, 0:2] = v + rng.uniform(-60, 60, 2)
+    return pose, ints, lidar, goals, ret
+
+
+def f32_inputs(pose, ints, lidar, goals, ret):
+    """Round the injected state to fp32 so that oracle and kernel start from IDENTICAL values."""
+    return (pose.astype(np.float32).astype(np.float64), ints, lidar.astype(np.float32).astype(np.float64),
+            goals.astype(np.float32).astype(np.float64), ret.astype(np.float32).astype(np.float64))
+
+
+def load_oracle_state(orc, pose, ints, lidar, goals, ret):
+    n = orc.n
+    orc.pose[:] = pose
+    orc.ints[:] = ints
+    orc.lidar[:] = -1.0
+    orc.lidar[:, :10] = lidar
+    orc.goals[:] = goals.reshape(n, 5, 2)
+    orc.ep_return[:] = ret
+    # history deque: older frames are unknowable for an injected state; newest frame = current pre-step frame
+    F = orc.frame
+    orc.hist[:] = -1.0
+    fr = np.zeros((n, F))
+    fr[:, 0:2] = pose[:, 0:2]
+    fr[:, 2] = ints[:, 0]
+    fr[:, 3] = pose[:, 2]
+    g = goals.reshape(n, 5, 2)
+    d = np.sqrt(((g - pose[:, None, 0:2]) ** 2).sum(-1))
+    alive = (ints[:, 1:2] >> np.arange(5)[None]) & 1
+    d = np.where(alive == 1, d, np.inf)
+    k = d.argmin(1)
+    has = alive.any(1)
+    fr[:, 4] = np.where(has, g[np.arange(n), k, 0], -1.0)
+    fr[:, 5] = np.where(has, g[np.arange(n), k, 1], -1.0)
+    fr[:, 6:16] = lidar
+    orc.hist[:, -F:] = fr
+
+
+def compare_steps(ref, got_obs, got_rew, got_done, margin_thr=1e-3, rel_tol=REL_TOL, label=""):
+    """ref: oracle dict of [K,N,...]; got_*: numpy [K,N,...] from the kernel.  An env is compared up to (not
+    including) the first step at which any margin drops below `margin_thr` (after a grazing decision the two
+    trajectories may legitimately diverge).  Returns a report dict; raises AssertionError on mismatch."""
+    K, N = ref["reward"].shape
+    mg = ref["margins"]
+    F = got_obs.shape[-1]
+    nb = 10
+    graze = (mg[:, :, :4].min(-1) < margin_thr) | (mg[:, :, M_RAY0:M_RAY0 + nb].min(-1) < margin_thr)
+    # valid[k, e]: no grazing at any step <= k
+    valid = np.cumsum(graze, axis=0) == 0
+    n_cmp = int(valid.sum())
+    tol = rel_tol * np.maximum(1.0, np.abs(ref["obs"]))
+    err = np.abs(got_obs.astype(np.float64) - ref["obs"])
+    bad_obs = (err > tol) & valid[:, :, None]
+    if bad_obs.any():
+        k, e, j = np.argwhere(bad_obs)[0]
+        raise AssertionError("%s obs mismatch at step %d env %d slot %d: got %r ref %r (margins %r)"
+                             % (label, k, e, j, got_obs[k, e, j], ref["obs"][k, e, j], mg[k, e, :14]))
+    bad_r = (np.abs(got_rew.astype(np.float64) - ref["reward"]) > 1e-6) & valid
+    if bad_r.any():
+        k, e = np.argwhere(bad_r)[0]
+        raise AssertionError("%s reward mismatch at step %d env %d: got %r ref %r" % (label, k, e, got_rew[k, e], ref["reward"][k, e]))
+    bad_d = (got_done.astype(bool) != ref["done"].astype(bool)) & valid
+    if bad_d.any():
+        k, e = np.argwhere(bad_d)[0]
+        raise AssertionError("%s done mismatch at step %d env %d: got %r ref %r flags %r margins %r"
+                             % (label, k, e, got_done[k, e], ref["done"][k, e], ref["flags"][k, e], mg[k, e, :4]))
+    return dict(compared=n_cmp, total=K * N, excluded_frac=1.0 - n_cmp / float(K * N),
+                max_rel_err=float((err / np.maximum(1.0, np.abs(ref["obs"])))[valid].max()) if n_cmp else 0.0,
+                frame=F)
