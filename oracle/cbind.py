@@ -165,6 +165,7 @@ class OracleEnv(object):
         self.obs_dim = self.frame * history
         self.maxbeams = self.L.orc_max_beams()
         self.mstride = self.L.orc_margin_stride()
+        self.cond_offset = 4 + self.maxbeams
         self.pose = np.zeros((self.n, 6))
         self.lidar = np.full((self.n, self.maxbeams), -1.0)
         self.goals = np.zeros((self.n, 5, 2))

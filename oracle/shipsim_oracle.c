@@ -228,7 +228,7 @@ static double poly_point_distance(const orc_poly *p, double px, double py)
     return outside ? min_dist : -min_dist;
 }
 
-typedef struct { int hit; double px, py, alpha, margin; } orc_seg_info;
+typedef struct { int hit; double px, py, alpha, margin, cond; } orc_seg_info;   /* cond = 1/|n.dir| of the accepted edge */
 
 /* CircleSegmentQuery (chipmunk_private.h) */
 static void circle_segment_query(double cx, double cy, double r1, double ax, double ay, double bx, double by,
@@ -263,7 +263,7 @@ static inline double dmax(double a, double b) { return a > b ? a : b; }
 static void poly_segment_query(const orc_poly *p, double ax, double ay, double bx, double by, double r2,
                                orc_seg_info *info)
 {
-    info->hit = 0; info->px = bx; info->py = by; info->alpha = 1.0; info->margin = INFINITY;
+    info->hit = 0; info->px = bx; info->py = by; info->alpha = 1.0; info->margin = INFINITY; info->cond = 1.0;
     const double nearest = poly_point_distance(p, ax, ay);
     info->margin = dmin(info->margin, fabs(nearest - r2));
     if (nearest <= r2) {               /* start inside (or within r): hit, alpha 0, point stays at b */
@@ -294,11 +294,12 @@ static void poly_segment_query(const orc_poly *p, double ax, double ay, double b
             info->px = qx - nx * r2;
             info->py = qy - ny * r2;
             info->alpha = t;
+            info->cond = len / dmax(an - bn, DBL_MIN);
         }
     }
     if (r2 > 0.0) {                    /* bevelled vertices */
         for (int i = 0; i < n; ++i) {
-            orc_seg_info ci = {0, bx, by, 1.0, INFINITY};
+            orc_seg_info ci = {0, bx, by, 1.0, INFINITY, 1.0};
             circle_segment_query(p->vx[i], p->vy[i], 0.0, ax, ay, bx, by, r2, &ci);
             if (ci.alpha < info->alpha) { info->hit = ci.hit; info->px = ci.px; info->py = ci.py; info->alpha = ci.alpha; }
         }
@@ -510,7 +511,7 @@ static void reset_env(const orc_config *c, const orc_bank *bank, const orc_state
 
 /* margins row layout: [0] |ship-bank SAT separation| (min over banks), [1] min_k |dist(goal_k)-r| over alive
  * goals, [2] out-of-bounds slack, [3] nearest-goal tie slack (new frame), [4+i] lidar ray i slack */
-#define ORC_MARGIN_STRIDE (4 + ORC_MAXBEAMS)
+#define ORC_MARGIN_STRIDE (4 + 2 * ORC_MAXBEAMS)   /* [4+MAXBEAMS+i] = conditioning 1/|n.dir| of ray i's accepted hit (1 if none) */
 /* flags bits */
 #define ORC_F_COLLIDING 1
 #define ORC_F_GOAL 2
@@ -536,6 +537,7 @@ static void step_env(const orc_config *c, const orc_derived *d, const orc_bank *
     load_bank_poly(c, bank, scen, 1, &bankp[1]);
     double mg[ORC_MARGIN_STRIDE];
     for (int i = 0; i < ORC_MARGIN_STRIDE; ++i) mg[i] = INFINITY;
+    for (int i = 0; i < ORC_MAXBEAMS; ++i) mg[4 + ORC_MAXBEAMS + i] = 1.0;
 
     /* -- ShipGame.handle_discrete_action (game.py:140-153), Ship.move_forward / rotate (models.py:129-146) */
     double fx = 0.0, fy = 0.0, torque = 0.0;
@@ -570,6 +572,7 @@ static void step_env(const orc_config *c, const orc_derived *d, const orc_bank *
                 mg[4 + i] = dmin(mg[4 + i], info.margin);
                 if (info.hit) {
                     lidar[i] = sqrt((info.px - ox) * (info.px - ox) + (info.py - oy) * (info.py - oy));
+                    mg[4 + ORC_MAXBEAMS + i] = info.cond;
                     break;
                 }
             }

@@ -200,7 +200,7 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
             return fail(SHIPSIM_ERR_ARG, "hull vertex count out of range [3, min(maxv, 32)]");
         dev_maxv = std::max(dev_maxv, (int)hull_n[i]);
     }
-    const int stride4 = kBankHeader4 + 2 * dev_maxv * 2;
+    const int stride4 = kBankHeader4 + 2 * dev_maxv;
     std::vector<float4> host((size_t)n_scen * stride4, make_float4(0.f, 0.f, 0.f, 0.f));
     for (int s = 0; s < n_scen; ++s) {
         float4 *rec = host.data() + (size_t)s * stride4;
@@ -215,19 +215,12 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
             }
             if (!(area2 > 0)) return fail(SHIPSIM_ERR_ARG, "bank hulls must be convex and counter-clockwise");
             rec[b] = make_float4(round_down(l), round_down(bo), round_up(r), round_up(t));
-            float4 *E = rec + kBankHeader4 + b * dev_maxv * 2;
-            for (int i = 0; i < dev_maxv; ++i) {
-                if (i < n) {
-                    const double ax = v[2 * ((i + n - 1) % n)], ay = v[2 * ((i + n - 1) % n) + 1], bx = v[2 * i], by = v[2 * i + 1];
-                    const double ex = bx - ax, ey = by - ay, ln = std::sqrt(ex * ex + ey * ey);
-                    if (!(ln > 0)) return fail(SHIPSIM_ERR_ARG, "degenerate hull edge");
-                    const double nx = ey / ln, ny = -ex / ln;                 // cpvrperp: outward for CCW
-                    E[2 * i] = make_float4((float)nx, (float)ny, (float)(nx * bx + ny * by), (float)(nx * ay - ny * ax));
-                    E[2 * i + 1] = make_float4((float)(nx * by - ny * bx), (float)bx, (float)by, 0.f);
-                } else {                                                      // padding: see shipsim_device.cuh
-                    E[2 * i] = make_float4(0.f, 0.f, 1.0e30f, 0.f);
-                    E[2 * i + 1] = make_float4(0.f, (float)v[0], (float)v[1], 0.f);
-                }
+            float4 *E = rec + kBankHeader4 + b * dev_maxv;
+            for (int i = 0; i < n; ++i) {
+                const double ax = v[2 * ((i + n - 1) % n)], ay = v[2 * ((i + n - 1) % n) + 1], bx = v[2 * i], by = v[2 * i + 1];
+                const double ex = bx - ax, ey = by - ay, ln = std::sqrt(ex * ex + ey * ey);
+                if (!(ln > 0)) return fail(SHIPSIM_ERR_ARG, "degenerate hull edge");
+                E[i] = make_float4((float)(ey / ln), (float)(-ex / ln), (float)bx, (float)by);   // cpvrperp: outward for CCW
             }
         }
         const double *g = goals_xy + (size_t)s * 10;

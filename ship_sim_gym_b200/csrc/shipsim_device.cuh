@@ -20,11 +20,11 @@ constexpr int kStatLen = 16;
 constexpr int kBankHeader4 = 6;     // float4s before the edge records of a scenario
 
 // Scenario record (float4 units): [0] aabb bank0 (l,b,r,t)  [1] aabb bank1  [2] goal0.xy goal1.xy
-// [3] goal2.xy goal3.xy  [4] goal4.xy, bits(n0), bits(n1)  [5] reserved; then per bank b, edge i:
-// [6 + (b*maxv+i)*2 + 0] = nx, ny, c = n.v_i, tmin = cross(n, v_{i-1})
-// [6 + (b*maxv+i)*2 + 1] = tmax = cross(n, v_i), v_i.x, v_i.y, 0
-// Plane i is the edge v_{i-1} -> v_i with outward normal n (Chipmunk's cpSplittingPlane {v0 = v_i, n}).
-// Padding edges (i >= n_b): n = 0, c = +huge (never separating, never hit), vertex = copy of v_0.
+// [3] goal2.xy goal3.xy  [4] goal4.xy, bits(n0), bits(n1)  [5] reserved; then per bank b, edge i < n_b:
+// [6 + b*maxv + i] = nx, ny, v_i.x, v_i.y
+// Plane i is the edge v_{i-1} -> v_i with outward unit normal n (Chipmunk's cpSplittingPlane {v0 = v_i, n}).
+// All plane tests are evaluated RELATIVE to the vertex (n.(p - v_i)), never as n.p - n.v_i: world coordinates
+// are O(1000) and fp32 would lose ~1e-4 to cancellation; differences of nearby points are (nearly) exact.
 
 struct StepParams {
     float4 *state;               // [kPlanes][N]
@@ -168,21 +168,23 @@ __device__ __forceinline__ void lidar_query(const StepParams &p, const float4 *_
         const float wy = p.ship_lx[j] * s + p.ship_ly[j] * c;
         minx = fminf(minx, wx); maxx = fmaxf(maxx, wx); miny = fminf(miny, wy); maxy = fmaxf(maxy, wy);
     }
-    const float ox = r.x + 0.5f * (maxx - minx);
-    const float oy = r.y + 0.5f * (maxy - miny);
+    const float hx = 0.5f * (maxx - minx), hy = 0.5f * (maxy - miny);
+    const float ox = r.x + hx, oy = r.y + hy;
     const float L = p.lidar_len;
+    const float4 hdr = __ldg(sc + 4);
     unsigned pending = (1u << kBeams) - 1u;
 #pragma unroll 1
     for (int b = 0; b < 2; ++b) {
         const float4 bb = __ldg(sc + b);
         if (ox + L < bb.x || ox - L > bb.z || oy + L < bb.y || oy - L > bb.w) continue;   // fan cannot reach the bank
-        const float4 *E = sc + kBankHeader4 + b * p.maxv * 2;
+        const float4 *E = sc + kBankHeader4 + b * p.maxv;
+        const int n = __float_as_int(b == 0 ? hdr.z : hdr.w);
         // pass 1: cpShapePointQuery "inside" test + edges whose plane is within reach in front of the origin
         unsigned live = 0u;
         bool inside = true;
-        for (int i = 0; i < p.maxv; ++i) {
-            const float4 e0 = __ldg(E + 2 * i);
-            const float d = e0.x * ox + e0.y * oy - e0.z;
+        for (int i = 0; i < n; ++i) {
+            const float4 e = __ldg(E + i);
+            const float d = e.x * ((r.x - e.z) + hx) + e.y * ((r.y - e.w) + hy);      // n.(origin - v_i)
             inside = inside && (d <= 0.f);
             if (d >= 0.f && d <= L) live |= 1u << i;
         }
@@ -196,19 +198,29 @@ __device__ __forceinline__ void lidar_query(const StepParams &p, const float4 *_
         while (live) {
             const int i = __ffs(live) - 1;
             live &= live - 1u;
-            const float4 e0 = __ldg(E + 2 * i);
-            const float4 e1 = __ldg(E + 2 * i + 1);
-            const float d = e0.x * ox + e0.y * oy - e0.z;
-            const float ta = e0.x * oy - e0.y * ox;                   // cross(n, origin)
+            const float4 e = __ldg(E + i);
+            const float4 ep = __ldg(E + (i == 0 ? n - 1 : i - 1));
+            // The hit distance is d / (-n.dir): any error of d is amplified by 1/cos(incidence).  The stored fp32
+            // normal is only good to ~6e-8 rad, which over a 1000-unit edge is 6e-5 of d -- so for the (few) live
+            // edges the normal is rebuilt in double from the two fp32 vertices (exactly what the reference's
+            // double-precision planes are made of) and d is formed in double.  B200 runs FP64 at half FP32 rate.
+            const double exd = (double)e.z - (double)ep.z, eyd = (double)e.w - (double)ep.w;
+            const double inv = rsqrt(exd * exd + eyd * eyd);
+            const double nxd = eyd * inv, nyd = -exd * inv;
+            const double qxd = ((double)r.x - (double)e.z) + (double)hx, qyd = ((double)r.y - (double)e.w) + (double)hy;
+            const float d = (float)(nxd * qxd + nyd * qyd);
+            const float ta = (float)(nxd * qyd - nyd * qxd);                          // cross(n, origin - v_i)
+            const float tmin = -(float)((exd * exd + eyd * eyd) * inv);               // cross(n, v_{i-1} - v_i) = -|edge|
+            const float enx = (float)nxd, eny = (float)nyd;
 #pragma unroll
             for (int k = 0; k < kBeams; ++k) {
                 const float dx = c * p.ray_c[k] - s * p.ray_s[k];     // cos(angle + a_k)
                 const float dy = s * p.ray_c[k] + c * p.ray_s[k];
-                const float denom = -L * (e0.x * dx + e0.y * dy);     // an - bn
+                const float denom = -L * (enx * dx + eny * dy);       // an - bn
                 float t;
                 if (denom > 0.f) t = d / denom; else t = (d == 0.f) ? 0.f : 2.f;   // d / max(an-bn, DBL_MIN)
-                const float tang = ta + t * L * (e0.x * dy - e0.y * dx);           // cross(n, lerp(a,b,t))
-                const bool ok = (t <= 1.f) && (tang >= e0.w) && (tang <= e1.x) && (pending >> k & 1u);
+                const float tang = ta + t * L * (enx * dy - eny * dx);             // cross(n, lerp(a,b,t) - v_i)
+                const bool ok = (t <= 1.f) && (tang >= tmin) && (tang <= 0.f) && (pending >> k & 1u);
                 if (ok) { r.lid[k] = t * L; hit |= 1u << k; }
             }
         }
@@ -219,29 +231,31 @@ __device__ __forceinline__ void lidar_query(const StepParams &p, const float4 *_
 // ---------------------------------------------------------------------------------------------- overlap tests
 // cpSpaceStep narrow phase at the post-integration pose.  Poly-vs-poly contact <=> no separating axis among
 // the edge normals of both convex polygons (touching counts: GJK distance <= 0).
-__device__ __forceinline__ bool ship_touches_bank(const StepParams &p, const float4 *__restrict__ sc, int b,
-                                                  const float (&px)[kShipVerts], const float (&py)[kShipVerts],
+__device__ __forceinline__ bool ship_touches_bank(const StepParams &p, const float4 *__restrict__ sc, int b, int n,
+                                                  float x, float y, const float (&rx)[kShipVerts], const float (&ry)[kShipVerts],
                                                   float c, float s, float sminx, float sminy, float smaxx, float smaxy)
 {
+    // rx, ry: hull vertices relative to the body origin (x, y); s* : world AABB of the hull
     const float4 bb = __ldg(sc + b);
     if (sminx > bb.z || smaxx < bb.x || sminy > bb.w || smaxy < bb.y) return false;     // cpBBIntersects (inclusive)
-    const float4 *E = sc + kBankHeader4 + b * p.maxv * 2;
-    for (int i = 0; i < p.maxv; ++i) {               // bank edge normals
-        const float4 e0 = __ldg(E + 2 * i);
-        float m = e0.x * px[0] + e0.y * py[0];
+    const float4 *E = sc + kBankHeader4 + b * p.maxv;
+    for (int i = 0; i < n; ++i) {                    // bank edge normals
+        const float4 e = __ldg(E + i);
+        const float base = e.x * (x - e.z) + e.y * (y - e.w);
+        float m = e.x * rx[0] + e.y * ry[0];
 #pragma unroll
-        for (int k = 1; k < kShipVerts; ++k) m = fminf(m, e0.x * px[k] + e0.y * py[k]);
-        if (m - e0.z > 0.f) return false;
+        for (int k = 1; k < kShipVerts; ++k) m = fminf(m, e.x * rx[k] + e.y * ry[k]);
+        if (base + m > 0.f) return false;
     }
 #pragma unroll 1
     for (int j = 0; j < kShipVerts; ++j) {           // ship edge normals
         const float nx = p.ship_nx[j] * c - p.ship_ny[j] * s;
         const float ny = p.ship_nx[j] * s + p.ship_ny[j] * c;
-        const float off = nx * px[j] + ny * py[j];
+        const float off = nx * rx[j] + ny * ry[j];
         float m = 3.0e38f;
-        for (int i = 0; i < p.maxv; ++i) {
-            const float4 e1 = __ldg(E + 2 * i + 1);
-            m = fminf(m, nx * e1.y + ny * e1.z);
+        for (int i = 0; i < n; ++i) {
+            const float4 e = __ldg(E + i);
+            m = fminf(m, nx * (e.z - x) + ny * (e.w - y));
         }
         if (m - off > 0.f) return false;
     }

@@ -63,17 +63,19 @@ __global__ void __launch_bounds__(kThreadsT1) step_kernel_t1(const __grid_consta
             sincosf(r.th, &s, &c);
 
             // overlap tests at the new pose -> begin callbacks collide_ship / collide_goal (game.py:232-257)
-            float px[kShipVerts], py[kShipVerts];
+            float rx[kShipVerts], ry[kShipVerts];
             float sminx = 3.0e38f, sminy = 3.0e38f, smaxx = -3.0e38f, smaxy = -3.0e38f;
 #pragma unroll
             for (int j = 0; j < kShipVerts; ++j) {
-                px[j] = r.x + (p.ship_lx[j] * c - p.ship_ly[j] * s);
-                py[j] = r.y + (p.ship_lx[j] * s + p.ship_ly[j] * c);
-                sminx = fminf(sminx, px[j]); smaxx = fmaxf(smaxx, px[j]);
-                sminy = fminf(sminy, py[j]); smaxy = fmaxf(smaxy, py[j]);
+                rx[j] = p.ship_lx[j] * c - p.ship_ly[j] * s;
+                ry[j] = p.ship_lx[j] * s + p.ship_ly[j] * c;
+                sminx = fminf(sminx, r.x + rx[j]); smaxx = fmaxf(smaxx, r.x + rx[j]);
+                sminy = fminf(sminy, r.y + ry[j]); smaxy = fmaxf(smaxy, r.y + ry[j]);
             }
-            const bool colliding = ship_touches_bank(p, sc, 0, px, py, c, s, sminx, sminy, smaxx, smaxy)
-                                || ship_touches_bank(p, sc, 1, px, py, c, s, sminx, sminy, smaxx, smaxy);
+            const float4 hdr = __ldg(sc + 4);
+            const bool colliding =
+                ship_touches_bank(p, sc, 0, __float_as_int(hdr.z), r.x, r.y, rx, ry, c, s, sminx, sminy, smaxx, smaxy) ||
+                ship_touches_bank(p, sc, 1, __float_as_int(hdr.w), r.x, r.y, rx, ry, c, s, sminx, sminy, smaxx, smaxy);
             bool goal_reached = false;
 #pragma unroll
             for (int g = 0; g < kGoals; ++g) {

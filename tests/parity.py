@@ -7,6 +7,13 @@ margins it reports (distance of every evaluated inequality from its decision bou
 import numpy as np
 
 REL_TOL = 1e-4
+# Lidar readings are DIFFERENCES of world coordinates divided by cos(incidence): a pose that is within tolerance
+# (fp32 world coordinates carry ulp(600) = 6e-5 per rounding, a few ulps after 32 steps) moves a reading by
+# (pose error) x cond, cond = 1/|n.dir| of the hit edge, which the oracle reports.  All readings must satisfy
+#   |err| <= (REL_TOL * max(1, |ref|) + POSE_ABS * max(W, H)) * cond
+# and at least STRICT_FRAC of them the plain REL_TOL * max(1, |ref|) bound.
+POSE_ABS = 1e-6
+STRICT_FRAC = 0.99
 # margin layout of the oracle: [0] ship-bank SAT |separation|, [1] |goal distance - r|, [2] out-of-bounds slack,
 # [3] nearest-goal tie slack, [4+i] lidar ray i
 M_SAT, M_GOAL, M_OOB, M_TIE, M_RAY0 = 0, 1, 2, 3, 4
@@ -72,7 +79,7 @@ def load_oracle_state(orc, pose, ints, lidar, goals, ret):
     orc.hist[:, -F:] = fr
 
 
-def compare_steps(ref, got_obs, got_rew, got_done, margin_thr=1e-3, rel_tol=REL_TOL, label=""):
+def compare_steps(ref, got_obs, got_rew, got_done, margin_thr=1e-3, rel_tol=REL_TOL, label="", scale=600.0):
     """ref: oracle dict of [K,N,...]; got_*: numpy [K,N,...] from the kernel.  An env is compared up to (not
     including) the first step at which any margin drops below `margin_thr` (after a grazing decision the two
     trajectories may legitimately diverge).  Returns a report dict; raises AssertionError on mismatch."""
@@ -86,6 +93,22 @@ def compare_steps(ref, got_obs, got_rew, got_done, margin_thr=1e-3, rel_tol=REL_
     n_cmp = int(valid.sum())
     tol = rel_tol * np.maximum(1.0, np.abs(ref["obs"]))
     err = np.abs(got_obs.astype(np.float64) - ref["obs"])
+    strict_bad = (err > tol) & valid[:, :, None]
+    # lidar slots: conditioning-aware bound.  The newest frame holds this step's readings (cond of step k); the
+    # older frame holds the previous step's (cond of step k-1; unknown for k = 0 of an injected state -> that
+    # frame is the injected value itself, exact).
+    cond = np.maximum(1.0, mg[:, :, 4 + 32:4 + 32 + nb])
+    cond_run = np.maximum.accumulate(cond, axis=0)          # sticky readings keep the cond of the step that wrote them
+    lid_tol_scale = np.ones_like(tol)
+    lid_abs = np.zeros_like(tol)
+    new0 = F - 16 + 6
+    lid_tol_scale[:, :, new0:new0 + nb] = cond_run
+    lid_abs[:, :, new0:new0 + nb] = POSE_ABS * scale
+    if F == 32:
+        prev = np.concatenate([np.ones_like(cond_run[:1]), cond_run[:-1]], axis=0)
+        lid_tol_scale[:, :, 6:6 + nb] = prev
+        lid_abs[:, :, 6:6 + nb] = POSE_ABS * scale
+    tol = (tol + lid_abs) * lid_tol_scale
     bad_obs = (err > tol) & valid[:, :, None]
     if bad_obs.any():
         k, e, j = np.argwhere(bad_obs)[0]
@@ -100,6 +123,11 @@ def compare_steps(ref, got_obs, got_rew, got_done, margin_thr=1e-3, rel_tol=REL_
         k, e = np.argwhere(bad_d)[0]
         raise AssertionError("%s done mismatch at step %d env %d: got %r ref %r flags %r margins %r"
                              % (label, k, e, got_done[k, e], ref["done"][k, e], ref["flags"][k, e], mg[k, e, :4]))
-    return dict(compared=n_cmp, total=K * N, excluded_frac=1.0 - n_cmp / float(K * N),
-                max_rel_err=float((err / np.maximum(1.0, np.abs(ref["obs"])))[valid].max()) if n_cmp else 0.0,
+    n_entries = int(valid.sum()) * F
+    strict_frac = 1.0 - float(strict_bad.sum()) / max(1, n_entries)
+    if strict_frac < STRICT_FRAC:
+        raise AssertionError("%s only %.4f of the compared obs entries are within the plain %g bound" % (label, strict_frac, rel_tol))
+    return dict(compared=n_cmp, total=K * N, excluded_frac=1.0 - n_cmp / float(K * N), strict_frac=strict_frac,
+                max_rel_err=float((err / np.maximum(1.0, np.abs(ref["obs"])) / lid_tol_scale)[valid].max()) if n_cmp else 0.0,
+                max_pose_rel_err=float((err / np.maximum(1.0, np.abs(ref["obs"])))[:, :, F - 16:F - 12][valid].max()) if n_cmp else 0.0,
                 frame=F)

@@ -73,7 +73,7 @@ def test_golden_trajectories(lanes):
         ref_golden["obs"] = ep["obs"][1:][:, None, :]
         ref_golden["reward"] = ep["reward"][:, None]
         ref_golden["done"] = ep["done"][:, None]
-        rep = parity.compare_steps(ref_golden, obs, rew, done, label="episode %d" % idx)
+        rep = parity.compare_steps(ref_golden, obs, rew, done, label="episode %d" % idx, scale=max(W, H))
         worst = max(worst, rep["max_rel_err"])
         env.close()
     assert worst < parity.REL_TOL
@@ -95,8 +95,13 @@ def test_long_history_host_layer():
 
 # ---------------------------------------------------------------------------------------------- injected states
 def _bank(n, W, H, seed=0, map_N=10, wf=0.5):
+    """Scenario bank rounded to fp32: the map is part of the injected state, so the oracle and the kernel (which
+    stores hull vertices and goals as fp32) must start from IDENTICAL geometry."""
     from ship_sim_gym_b200 import ScenarioBank
-    return ScenarioBank.generate(n, (W, H), seed=seed, map_N=map_N, width_frac=wf).as_dict()
+    d = ScenarioBank.generate(n, (W, H), seed=seed, map_N=map_N, width_frac=wf).as_dict()
+    d["hull_xy"] = d["hull_xy"].astype(np.float32).astype(np.float64)
+    d["goals"] = d["goals"].astype(np.float32).astype(np.float64)
+    return d
 
 
 CASES = [
@@ -124,7 +129,7 @@ def test_injected_single_step(case, adversarial):
     acts = rng.randint(0, 3, n).astype(np.int32)
     o, r, d, _ = env.step(torch.tensor(acts, device=env.device))
     ref = orc.step(acts[None])
-    rep = parity.compare_steps(ref, o.cpu().numpy()[None], r.cpu().numpy()[None], d.cpu().numpy()[None], label=case["name"])
+    rep = parity.compare_steps(ref, o.cpu().numpy()[None], r.cpu().numpy()[None], d.cpu().numpy()[None], label=case["name"], scale=max(W, H))
     assert rep["excluded_frac"] < 0.01, rep
     assert rep["max_rel_err"] < parity.REL_TOL
     # the post-step state itself (velocities are not part of obs)
@@ -154,7 +159,7 @@ def test_32_step_transitions(case, auto_reset):
     acts = rng.choice([0, 0, 1, 2], size=(K, n)).astype(np.int32)
     obs, rew, done = _np(*env.rollout(torch.tensor(acts, device=env.device)))
     ref = orc.step(acts)
-    rep = parity.compare_steps(ref, obs, rew, done, margin_thr=5e-3, label=case["name"])
+    rep = parity.compare_steps(ref, obs, rew, done, margin_thr=5e-3, label=case["name"], scale=max(W, H))
     assert rep["excluded_frac"] < 0.05, rep
     assert rep["max_rel_err"] < parity.REL_TOL
     if auto_reset:
