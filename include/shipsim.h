@@ -92,8 +92,8 @@ typedef struct shipsim_config {
     float goal_radius;           /* game.py:82 (5)                                                   */
     float step_penalty;          /* ship_env.py:13 (-0.01)                                           */
     float spawn_y;               /* game.py:274 (25); spawn x is bounds_w/2                          */
-    int32_t lanes_per_env;       /* 0 = choose from num_envs; 1 = one thread per env; 8 = eight cooperating
-                                    lanes per env (small batches)                                    */
+    int32_t lanes_per_env;       /* cooperating lanes per env: 0 = choose from num_envs, else 1, 2, 4, 8, 16 or 32
+                                    (32 = one warp per env, for small latency-bound batches)         */
 } shipsim_config;
 
 typedef struct shipsim_handle shipsim_t;

@@ -23,7 +23,7 @@ struct shipsim_handle {
     int32_t *d_act = nullptr; float *d_obs = nullptr; float *d_rew = nullptr; uint8_t *d_done = nullptr;
     int stage_K = 0;
     int64_t launches = 0;
-    LaunchShape shape{1, kThreadsT1, 0};
+    LaunchShape shape{1, kThreads, 0};
 };
 
 static thread_local std::string g_err;
@@ -162,8 +162,11 @@ extern "C" int shipsim_create(const shipsim_config *cfg, int device, shipsim_t *
     if (!(cfg->dt > 0.f) || !(cfg->bounds_w > 0.f) || !(cfg->bounds_h > 0.f) || !(cfg->lidar_distance > 0.f) || cfg->max_steps < 1
         || cfg->max_steps >= (1 << 22))
         return fail(SHIPSIM_ERR_ARG, "dt, bounds, lidar_distance must be positive and 1 <= max_steps < 2^22");
-    if (cfg->lanes_per_env != 0 && cfg->lanes_per_env != 1 && cfg->lanes_per_env != 8)
-        return fail(SHIPSIM_ERR_ARG, "lanes_per_env must be 0, 1 or 8");
+    {
+        const int g = cfg->lanes_per_env;
+        if (g != 0 && g != 1 && g != 2 && g != 4 && g != 8 && g != 16 && g != 32)
+            return fail(SHIPSIM_ERR_ARG, "lanes_per_env must be 0 (auto), 1, 2, 4, 8, 16 or 32");
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SHIPSIM_ERR_CUDA, "no CUDA device: libshipsim has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(SHIPSIM_ERR_ARG, "bad device index");
@@ -175,7 +178,16 @@ extern "C" int shipsim_create(const shipsim_config *cfg, int device, shipsim_t *
     h->device = device;
     const int rc = derive_params(h);
     if (rc != SHIPSIM_OK) { delete h; return rc; }
-    h->lanes = cfg->lanes_per_env ? cfg->lanes_per_env : 1;
+    if (cfg->lanes_per_env) {
+        h->lanes = cfg->lanes_per_env;
+    } else {
+        // Auto: small batches are latency bound, so spend lanes on intra-env parallelism until the grid offers
+        // about kTargetWarps warps (148 SMs x 4 schedulers x a few warps each); large batches use one lane per env.
+        const long long kTargetWarps = 148LL * 4 * 6;
+        int g = 32;
+        while (g > 1 && (long long)cfg->num_envs * g / 32 > kTargetWarps) g >>= 1;
+        h->lanes = g;
+    }
     *out = h;
     return SHIPSIM_OK;
 }

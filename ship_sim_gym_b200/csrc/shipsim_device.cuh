@@ -3,7 +3,14 @@
 // New code, written for sm_100a.  It implements the transition spec of SURVEY.md Appendix A, which restates
 // ShipEnv.step (ship_gym/ship_env.py:136-156) and everything it reaches (game.py:140-153,185-195,232-257,
 // 333-349; models.py:39-76,129-146) plus the Chipmunk2D routines the reference delegates to.  fp32 state,
-// hull planes precomputed in double on the host.
+// hull planes rebuilt in double where conditioning demands it.
+//
+// Execution model: G lanes cooperate on one env (G = 1, 2, 4, 8, 16 or 32; 32/G envs per warp).  The lanes of a
+// group hold IDENTICAL copies of the env's scalar state, so the cheap serial parts (integrator, reward, done) are
+// computed redundantly with no communication, regular loops (bank edges) are strided over the group, and the
+// irregular heavy parts (ray-vs-live-edge tests, separating-axis tests) are executed by the WHOLE WARP for one
+// needy env at a time (loop over a ballot), which keeps control flow warp-uniform: the first thread-per-env
+// kernel ran with 7-9 of 32 lanes active (ncu, profiles/r01_v1_*.txt) because every lane took its own path.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -18,6 +25,7 @@ constexpr int kShipVerts = 5;
 constexpr int kStatSlots = 128;     // replicated accumulator rows (one 128-byte line each) to spread atomics
 constexpr int kStatLen = 16;
 constexpr int kBankHeader4 = 6;     // float4s before the edge records of a scenario
+constexpr unsigned kFull = 0xffffffffu;
 
 // Scenario record (float4 units): [0] aabb bank0 (l,b,r,t)  [1] aabb bank1  [2] goal0.xy goal1.xy
 // [3] goal2.xy goal3.xy  [4] goal4.xy, bits(n0), bits(n1)  [5] reserved; then per bank b, edge i < n_b:
@@ -84,6 +92,33 @@ __device__ __forceinline__ int random_action(const StepParams &p, long long gid,
 {
     const uint4 r = philox4x32_10(p.seed, (unsigned long long)gid, step, 1u);
     return (int)__umulhi(r.x, 3u);
+}
+
+// ---------------------------------------------------------------------------------------------- sin / cos
+// One sincos per env-step sits on the loop-carried critical path (pose -> overlap tests -> done -> reset -> pose).
+// Cody-Waite reduction by pi/2 (3 constants, exact for |x| < ~1e5, which bounds any reachable angle:
+// |w| <= ~1.4 rad/s * dt over at most max_steps steps) + the usual minimax polynomials on [-pi/4, pi/4];
+// ~1 ulp, no local-memory slow path in the hot loop (libdevice's Payne-Hanek branch is kept for huge angles).
+__device__ __forceinline__ void sincos_fast(float x, float &sn, float &cs)
+{
+    if (fabsf(x) > 1.0e5f) { sincosf(x, &sn, &cs); return; }
+    const float q = rintf(x * 0.636619772367581343f);          // 2/pi
+    float r = fmaf(q, -1.57079601287841796875f, x);
+    r = fmaf(q, -3.1391647326017846353352069854736e-07f, r);
+    r = fmaf(q, -5.3903029534742383771844745924903e-15f, r);
+    const int n = (int)q;
+    const float r2 = r * r;
+    float sp = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
+    sp = fmaf(sp, r2, -1.66666546e-1f);
+    sp = fmaf(sp * r2, r, r);
+    float cp = fmaf(r2, 2.44331571e-5f, -1.38873163e-3f);
+    cp = fmaf(cp, r2, 4.16666457e-2f);
+    cp = fmaf(cp, r2, -0.5f);
+    cp = fmaf(cp, r2, 1.0f);
+    const float s1 = (n & 1) ? cp : sp;
+    const float c1 = (n & 1) ? sp : cp;
+    sn = (n & 2) ? -s1 : s1;
+    cs = ((n + 1) & 2) ? -c1 : c1;
 }
 
 // ---------------------------------------------------------------------------------------------- state I/O
@@ -154,121 +189,16 @@ __device__ __forceinline__ void closest_goal(const EnvRegs &r, float &gx, float 
     }
 }
 
-// ---------------------------------------------------------------------------------------------- lidar
-// LiDAR.query (models.py:39-76) over cpShapeSegmentQuery / cpPolyShapeSegmentQuery (Chipmunk, r = 0).
-// Sampled at the PRE-integration pose (game.py:193 before :194).  Hits overwrite r.lid[i]; misses keep the
-// previous value (sticky vals, models.py:71).  First bank in list order that reports a hit wins (models.py:61-72).
-__device__ __forceinline__ void lidar_query(const StepParams &p, const float4 *__restrict__ sc, EnvRegs &r, float c, float s)
-{
-    // cached AABB of the rotated hull -> ray origin = body origin + half extents (models.py:51-53)
-    float minx = 0.f, maxx = 0.f, miny = 0.f, maxy = 0.f;      // hull vertex 0 is the body origin
-#pragma unroll
-    for (int j = 1; j < kShipVerts; ++j) {
-        const float wx = p.ship_lx[j] * c - p.ship_ly[j] * s;
-        const float wy = p.ship_lx[j] * s + p.ship_ly[j] * c;
-        minx = fminf(minx, wx); maxx = fmaxf(maxx, wx); miny = fminf(miny, wy); maxy = fmaxf(maxy, wy);
-    }
-    const float hx = 0.5f * (maxx - minx), hy = 0.5f * (maxy - miny);
-    const float ox = r.x + hx, oy = r.y + hy;
-    const float L = p.lidar_len;
-    const float4 hdr = __ldg(sc + 4);
-    unsigned pending = (1u << kBeams) - 1u;
-#pragma unroll 1
-    for (int b = 0; b < 2; ++b) {
-        const float4 bb = __ldg(sc + b);
-        if (ox + L < bb.x || ox - L > bb.z || oy + L < bb.y || oy - L > bb.w) continue;   // fan cannot reach the bank
-        const float4 *E = sc + kBankHeader4 + b * p.maxv;
-        const int n = __float_as_int(b == 0 ? hdr.z : hdr.w);
-        // pass 1: cpShapePointQuery "inside" test + edges whose plane is within reach in front of the origin
-        unsigned live = 0u;
-        bool inside = true;
-        for (int i = 0; i < n; ++i) {
-            const float4 e = __ldg(E + i);
-            const float d = e.x * ((r.x - e.z) + hx) + e.y * ((r.y - e.w) + hy);      // n.(origin - v_i)
-            inside = inside && (d <= 0.f);
-            if (d >= 0.f && d <= L) live |= 1u << i;
-        }
-        if (inside) {                    // start point inside the shape: alpha = 0, point stays at the ray end
-#pragma unroll
-            for (int i = 0; i < kBeams; ++i) if (pending >> i & 1u) r.lid[i] = L;
-            pending = 0u;
-            break;
-        }
-        unsigned hit = 0u;
-        while (live) {
-            const int i = __ffs(live) - 1;
-            live &= live - 1u;
-            const float4 e = __ldg(E + i);
-            const float4 ep = __ldg(E + (i == 0 ? n - 1 : i - 1));
-            // The hit distance is d / (-n.dir): any error of d is amplified by 1/cos(incidence).  The stored fp32
-            // normal is only good to ~6e-8 rad, which over a 1000-unit edge is 6e-5 of d -- so for the (few) live
-            // edges the normal is rebuilt in double from the two fp32 vertices (exactly what the reference's
-            // double-precision planes are made of) and d is formed in double.  B200 runs FP64 at half FP32 rate.
-            const double exd = (double)e.z - (double)ep.z, eyd = (double)e.w - (double)ep.w;
-            const double inv = rsqrt(exd * exd + eyd * eyd);
-            const double nxd = eyd * inv, nyd = -exd * inv;
-            const double qxd = ((double)r.x - (double)e.z) + (double)hx, qyd = ((double)r.y - (double)e.w) + (double)hy;
-            const float d = (float)(nxd * qxd + nyd * qyd);
-            const float ta = (float)(nxd * qyd - nyd * qxd);                          // cross(n, origin - v_i)
-            const float tmin = -(float)((exd * exd + eyd * eyd) * inv);               // cross(n, v_{i-1} - v_i) = -|edge|
-            const float enx = (float)nxd, eny = (float)nyd;
-#pragma unroll
-            for (int k = 0; k < kBeams; ++k) {
-                const float dx = c * p.ray_c[k] - s * p.ray_s[k];     // cos(angle + a_k)
-                const float dy = s * p.ray_c[k] + c * p.ray_s[k];
-                const float denom = -L * (enx * dx + eny * dy);       // an - bn
-                float t;
-                if (denom > 0.f) t = d / denom; else t = (d == 0.f) ? 0.f : 2.f;   // d / max(an-bn, DBL_MIN)
-                const float tang = ta + t * L * (enx * dy - eny * dx);             // cross(n, lerp(a,b,t) - v_i)
-                const bool ok = (t <= 1.f) && (tang >= tmin) && (tang <= 0.f) && (pending >> k & 1u);
-                if (ok) { r.lid[k] = t * L; hit |= 1u << k; }
-            }
-        }
-        pending &= ~hit;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------- overlap tests
-// cpSpaceStep narrow phase at the post-integration pose.  Poly-vs-poly contact <=> no separating axis among
-// the edge normals of both convex polygons (touching counts: GJK distance <= 0).
-__device__ __forceinline__ bool ship_touches_bank(const StepParams &p, const float4 *__restrict__ sc, int b, int n,
-                                                  float x, float y, const float (&rx)[kShipVerts], const float (&ry)[kShipVerts],
-                                                  float c, float s, float sminx, float sminy, float smaxx, float smaxy)
-{
-    // rx, ry: hull vertices relative to the body origin (x, y); s* : world AABB of the hull
-    const float4 bb = __ldg(sc + b);
-    if (sminx > bb.z || smaxx < bb.x || sminy > bb.w || smaxy < bb.y) return false;     // cpBBIntersects (inclusive)
-    const float4 *E = sc + kBankHeader4 + b * p.maxv;
-    for (int i = 0; i < n; ++i) {                    // bank edge normals
-        const float4 e = __ldg(E + i);
-        const float base = e.x * (x - e.z) + e.y * (y - e.w);
-        float m = e.x * rx[0] + e.y * ry[0];
-#pragma unroll
-        for (int k = 1; k < kShipVerts; ++k) m = fminf(m, e.x * rx[k] + e.y * ry[k]);
-        if (base + m > 0.f) return false;
-    }
-#pragma unroll 1
-    for (int j = 0; j < kShipVerts; ++j) {           // ship edge normals
-        const float nx = p.ship_nx[j] * c - p.ship_ny[j] * s;
-        const float ny = p.ship_nx[j] * s + p.ship_ny[j] * c;
-        const float off = nx * rx[j] + ny * ry[j];
-        float m = 3.0e38f;
-        for (int i = 0; i < n; ++i) {
-            const float4 e = __ldg(E + i);
-            m = fminf(m, nx * (e.z - x) + ny * (e.w - y));
-        }
-        if (m - off > 0.f) return false;
-    }
-    return true;
-}
-
 // Circle-vs-poly contact (CircleToPoly): distance(goal centre, ship polygon) <= goal radius, evaluated in the
 // body frame where the hull is constant.  cpPolyShapePointQuery semantics: inside => negative distance.
-__device__ __forceinline__ bool goal_touches_ship(const StepParams &p, float qx, float qy)
+__device__ __forceinline__ bool goal_culled(const StepParams &p, float qx, float qy)
 {
     const float rr = p.goal_r;
-    if (qx < p.ship_aabb[0] - rr || qx > p.ship_aabb[2] + rr || qy < p.ship_aabb[1] - rr || qy > p.ship_aabb[3] + rr)
-        return false;
+    return qx < p.ship_aabb[0] - rr || qx > p.ship_aabb[2] + rr || qy < p.ship_aabb[1] - rr || qy > p.ship_aabb[3] + rr;
+}
+
+__device__ __forceinline__ bool goal_touches_ship(const StepParams &p, float qx, float qy)
+{
     bool outside = false;
     float best = 3.0e38f;
 #pragma unroll
@@ -277,12 +207,15 @@ __device__ __forceinline__ bool goal_touches_ship(const StepParams &p, float qx,
         const float ax = p.ship_lx[j0], ay = p.ship_ly[j0], bx = p.ship_lx[j], by = p.ship_ly[j];
         outside = outside || (p.ship_nx[j] * (qx - bx) + p.ship_ny[j] * (qy - by) > 0.f);
         const float ex = ax - bx, ey = ay - by;                       // cpClosetPointOnSegment
-        float t = (ex * (qx - bx) + ey * (qy - by)) / (ex * ex + ey * ey);
+        float t = __fdividef(ex * (qx - bx) + ey * (qy - by), ex * ex + ey * ey);
         t = fminf(fmaxf(t, 0.f), 1.f);
         const float cx = bx + ex * t - qx, cy = by + ey * t - qy;
         best = fminf(best, cx * cx + cy * cy);
     }
-    return !outside || best <= rr * rr;
+    return !outside || best <= p.goal_r * p.goal_r;
 }
+
+// order-preserving float <-> int map for __reduce_min_sync
+__device__ __forceinline__ int f2ord(float f) { const int k = __float_as_int(f); return k ^ ((k >> 31) & 0x7fffffff); }
 
 }  // namespace shipsim

@@ -6,7 +6,7 @@
 namespace shipsim {
 
 struct StepParams;
-constexpr int kThreadsT1 = 128;
+constexpr int kThreads = 128;
 
 struct LaunchShape { int lanes_per_env, threads, blocks; };
 
