@@ -141,6 +141,9 @@ static int derive_params(shipsim_handle *h)
         l = std::min(l, v.x); r = std::max(r, v.x); b = std::min(b, v.y); t = std::max(t, v.y);
     }
     p.ship_aabb[0] = (float)l; p.ship_aabb[1] = (float)b; p.ship_aabb[2] = (float)r; p.ship_aabb[3] = (float)t;
+    double rmax = 0;
+    for (auto &v : hull) rmax = std::max(rmax, std::sqrt(v.x * v.x + v.y * v.y));
+    p.goal_cull_r2 = (float)((rmax + c.goal_radius) * (rmax + c.goal_radius) * 1.0001);
     p.acc_dt = (float)((double)c.thrust / c.mass * c.dt);
     p.ang_dt = (float)((double)c.thrust / moment * c.dt);
     // lidar fan (models.py:48-49,62)
@@ -148,6 +151,7 @@ static int derive_params(shipsim_handle *h)
     const double delta = ((double)c.lidar_spread_deg / c.lidar_beams) * deg;
     const double start = (90.0 - (double)c.lidar_spread_deg / 2.0) * deg;
     for (int i = 0; i < kBeams; ++i) { p.ray_c[i] = (float)std::cos(start + delta * i); p.ray_s[i] = (float)std::sin(start + delta * i); }
+    p.fan_is_sector = (delta * (kBeams - 1) < 3.1) && (delta > 0) ? 1 : 0;
     return SHIPSIM_OK;
 }
 

@@ -57,6 +57,8 @@ struct StepParams {
     float ship_lx[kShipVerts], ship_ly[kShipVerts];  // body-frame hull, CCW (models.py:6,88 through cpConvexHull)
     float ship_nx[kShipVerts], ship_ny[kShipVerts];  // body-frame outward normal of edge j-1 -> j
     float ship_aabb[4];                              // body-frame l,b,r,t of the hull
+    float goal_cull_r2;                              // (max |hull vertex| + goal radius)^2: bounding circle about the body origin
+    int fan_is_sector;                               // the 10 rays span less than pi: their box is that of a circular sector
 };
 
 struct EnvRegs {
