@@ -18,6 +18,8 @@ struct shipsim_handle {
     int device = 0;
     StepParams p;
     float4 *d_bank = nullptr;
+    EdgeD *d_edges = nullptr;
+    uint4 *d_grid = nullptr;
     int lanes = 1;
     // staging for shipsim_step_host (allocated on first use, sized for the largest K seen)
     int32_t *d_act = nullptr; float *d_obs = nullptr; float *d_rew = nullptr; uint8_t *d_done = nullptr;
@@ -138,6 +140,7 @@ static int derive_params(shipsim_handle *h)
         const double ex = v.x - a.x, ey = v.y - a.y, ln = std::sqrt(ex * ex + ey * ey);
         p.ship_lx[j] = (float)v.x; p.ship_ly[j] = (float)v.y;
         p.ship_nx[j] = (float)(ey / ln); p.ship_ny[j] = (float)(-ex / ln);
+        p.ship_off[j] = (float)((ey / ln) * v.x + (-ex / ln) * v.y);
         l = std::min(l, v.x); r = std::max(r, v.x); b = std::min(b, v.y); t = std::max(t, v.y);
     }
     p.ship_aabb[0] = (float)l; p.ship_aabb[1] = (float)b; p.ship_aabb[2] = (float)r; p.ship_aabb[3] = (float)t;
@@ -151,7 +154,12 @@ static int derive_params(shipsim_handle *h)
     const double delta = ((double)c.lidar_spread_deg / c.lidar_beams) * deg;
     const double start = (90.0 - (double)c.lidar_spread_deg / 2.0) * deg;
     for (int i = 0; i < kBeams; ++i) { p.ray_c[i] = (float)std::cos(start + delta * i); p.ray_s[i] = (float)std::sin(start + delta * i); }
-    p.fan_is_sector = (delta * (kBeams - 1) < 3.1) && (delta > 0) ? 1 : 0;
+    // reach grid: kGridN x kGridN cells over the bounds plus a pad (the ray origin of a live env lies within
+    // [0, W + ship extent]); the border cells are unbounded
+    const double pad = 32.0;
+    p.gridp.x0 = (float)(-pad); p.gridp.y0 = (float)(-pad);
+    p.gridp.inv_cx = (float)(kGridN / (c.bounds_w + 2.0 * pad));
+    p.gridp.inv_cy = (float)(kGridN / (c.bounds_h + 2.0 * pad));
     return SHIPSIM_OK;
 }
 
@@ -200,7 +208,7 @@ extern "C" int shipsim_destroy(shipsim_t *h)
 {
     if (!h) return SHIPSIM_OK;
     DeviceGuard g(h->device);
-    cudaFree(h->d_bank); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
+    cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
     delete h;
     return SHIPSIM_OK;
 }
@@ -218,11 +226,18 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
     }
     const int stride4 = kBankHeader4 + 2 * dev_maxv;
     std::vector<float4> host((size_t)n_scen * stride4, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<EdgeD> edges((size_t)n_scen * 2 * dev_maxv);
+    std::memset(edges.data(), 0, edges.size() * sizeof(EdgeD));
+    // the device geometry is the fp32-rounded polygon: every derived quantity (fp32 planes, double planes, reach
+    // grid) is computed in double from the ROUNDED vertices, so the representations agree with each other
+    std::vector<double> rxy((size_t)n_scen * 2 * dev_maxv * 2, 0.0);
     for (int s = 0; s < n_scen; ++s) {
         float4 *rec = host.data() + (size_t)s * stride4;
         for (int b = 0; b < 2; ++b) {
-            const double *v = hull_xy + ((size_t)s * 2 + b) * maxv * 2;
+            const double *vin = hull_xy + ((size_t)s * 2 + b) * maxv * 2;
+            double *v = rxy.data() + ((size_t)s * 2 + b) * dev_maxv * 2;
             const int n = hull_n[s * 2 + b];
+            for (int i = 0; i < 2 * n; ++i) v[i] = (double)(float)vin[i];
             double l = 1e300, bo = 1e300, r = -1e300, t = -1e300, area2 = 0;
             for (int i = 0; i < n; ++i) {
                 const double ax = v[2 * ((i + n - 1) % n)], ay = v[2 * ((i + n - 1) % n) + 1], bx = v[2 * i], by = v[2 * i + 1];
@@ -232,11 +247,13 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
             if (!(area2 > 0)) return fail(SHIPSIM_ERR_ARG, "bank hulls must be convex and counter-clockwise");
             rec[b] = make_float4(round_down(l), round_down(bo), round_up(r), round_up(t));
             float4 *E = rec + kBankHeader4 + b * dev_maxv;
+            EdgeD *ED = edges.data() + ((size_t)s * 2 + b) * dev_maxv;
             for (int i = 0; i < n; ++i) {
                 const double ax = v[2 * ((i + n - 1) % n)], ay = v[2 * ((i + n - 1) % n) + 1], bx = v[2 * i], by = v[2 * i + 1];
                 const double ex = bx - ax, ey = by - ay, ln = std::sqrt(ex * ex + ey * ey);
                 if (!(ln > 0)) return fail(SHIPSIM_ERR_ARG, "degenerate hull edge");
                 E[i] = make_float4((float)(ey / ln), (float)(-ex / ln), (float)bx, (float)by);   // cpvrperp: outward for CCW
+                ED[i].nx = ey / ln; ED[i].ny = -ex / ln; ED[i].vx = (float)bx; ED[i].vy = (float)by; ED[i].len = (float)ln;
             }
         }
         const double *g = goals_xy + (size_t)s * 10;
@@ -247,15 +264,40 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
         std::memcpy(&g2.z, &n0, 4); std::memcpy(&g2.w, &n1, 4);
         rec[4] = g2;
     }
+    if (n_scen >= (1 << 28)) return fail(SHIPSIM_ERR_ARG, "too many scenarios");
     DeviceGuard g(h->device);
     float4 *d = nullptr;
-    CU(cudaMalloc(&d, host.size() * sizeof(float4)));
-    cudaError_t e = cudaMemcpy(d, host.data(), host.size() * sizeof(float4), cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) { cudaFree(d); return fail(SHIPSIM_ERR_CUDA, cudaGetErrorString(e)); }
-    CU(cudaDeviceSynchronize());           // no launch may still be reading the old bank
-    cudaFree(h->d_bank);
-    h->d_bank = d;
-    h->p.bank = d; h->p.n_scen = n_scen; h->p.maxv = dev_maxv; h->p.scen_stride4 = stride4;
+    EdgeD *de = nullptr;
+    uint4 *dg = nullptr;
+    double *dxy = nullptr;
+    int *dn = nullptr;
+    const size_t grid_cells = (size_t)n_scen * kGridN * kGridN;
+    auto cleanup = [&]() { cudaFree(d); cudaFree(de); cudaFree(dg); cudaFree(dxy); cudaFree(dn); };
+    cudaError_t e = cudaMalloc(&d, host.size() * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&de, edges.size() * sizeof(EdgeD));
+    if (e == cudaSuccess) e = cudaMalloc(&dg, grid_cells * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMalloc(&dxy, rxy.size() * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&dn, (size_t)n_scen * 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(d, host.data(), host.size() * sizeof(float4), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(de, edges.data(), edges.size() * sizeof(EdgeD), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dxy, rxy.data(), rxy.size() * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dn, hull_n, (size_t)n_scen * 2 * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        // reach grid, built on the device in double (one thread per cell)
+        const double pad = -(double)h->p.gridp.x0;
+        const double cw = ((double)h->cfg.bounds_w + 2.0 * pad) / kGridN, ch = ((double)h->cfg.bounds_h + 2.0 * pad) / kGridN;
+        const double margin = 0.05 + 1e-4 * std::max((double)h->cfg.bounds_w, (double)h->cfg.bounds_h);
+        const double reach = std::max((double)h->cfg.lidar_distance, std::sqrt(cw * cw + ch * ch)) + margin;
+        e = launch_build_grid(dxy, dn, n_scen, dev_maxv, (double)h->p.gridp.x0, (double)h->p.gridp.y0, cw, ch, reach, margin, dg, 0);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();           // also: no launch may still be reading the old bank
+    if (e != cudaSuccess) { cleanup(); return fail(SHIPSIM_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaFree(dxy); cudaFree(dn);
+    cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid);
+    h->d_bank = d; h->d_edges = de; h->d_grid = dg;
+    h->p.bank = d; h->p.edges_d = de; h->p.grid = dg;
+    h->p.n_scen = n_scen; h->p.maxv = dev_maxv; h->p.scen_stride4 = stride4;
+    h->launches++;
     return SHIPSIM_OK;
 }
 

@@ -25,7 +25,29 @@ constexpr int kShipVerts = 5;
 constexpr int kStatSlots = 128;     // replicated accumulator rows (one 128-byte line each) to spread atomics
 constexpr int kStatLen = 16;
 constexpr int kBankHeader4 = 6;     // float4s before the edge records of a scenario
+constexpr int kGridN = 32;          // the reach grid has kGridN x kGridN cells per scenario
 constexpr unsigned kFull = 0xffffffffu;
+
+// Double-precision plane of one bank edge, used only for LIVE ray/edge pairs (32 bytes = two 16-byte loads).
+// A lidar reading is d / (-n.dir): an error of d is amplified by 1/cos(incidence), and an fp32 normal (6e-8 rad)
+// swings d by 6e-5 over a 1000-unit edge, so live edges use the double plane the reference's cpSplittingPlane
+// holds.  Built on the host from the SAME fp32-rounded vertices the fp32 records carry.
+struct EdgeD {
+    double nx, ny;                  // outward unit normal of the edge v_{i-1} -> v_i
+    float vx, vy;                   // v_i
+    float len;                      // |v_i - v_{i-1}|
+    float pad;
+};
+
+// Reach grid: one uint4 per cell.  x / y: bit i set <=> edge i of bank 0 / 1 comes within max(lidar length, cell
+// diagonal) (+ margin) of the cell, i.e. the superset of edges a ray starting anywhere in the cell can touch;
+// z: bit b set <=> the cell may intersect the interior of bank b (then "origin inside the bank" <=> no candidate
+// plane has the origin in front of it; clear => the origin is certainly outside); w: reserved.
+// Border cells are unbounded (they stand for everything beyond the grid).
+struct GridParams {
+    float x0, y0;                   // lower-left corner of cell (0,0)
+    float inv_cx, inv_cy;           // 1 / cell size
+};
 
 // Scenario record (float4 units): [0] aabb bank0 (l,b,r,t)  [1] aabb bank1  [2] goal0.xy goal1.xy
 // [3] goal2.xy goal3.xy  [4] goal4.xy, bits(n0), bits(n1)  [5] reserved; then per bank b, edge i < n_b:
@@ -37,6 +59,9 @@ constexpr unsigned kFull = 0xffffffffu;
 struct StepParams {
     float4 *state;               // [kPlanes][N]
     const float4 *bank;          // packed scenario records
+    const EdgeD *edges_d;        // [n_scen][2][maxv] double planes
+    const uint4 *grid;           // [n_scen][kGridN*kGridN] reach grid
+    GridParams gridp;
     const void *actions;         // [K][N]
     float4 *obs;                 // [K][N][4*history]
     float *reward;               // [K][N]
@@ -56,9 +81,9 @@ struct StepParams {
     float ray_c[kBeams], ray_s[kBeams];              // cos/sin of radians(90 - spread/2 + i*spread/n) (models.py:48-49,62)
     float ship_lx[kShipVerts], ship_ly[kShipVerts];  // body-frame hull, CCW (models.py:6,88 through cpConvexHull)
     float ship_nx[kShipVerts], ship_ny[kShipVerts];  // body-frame outward normal of edge j-1 -> j
-    float ship_aabb[4];                              // body-frame l,b,r,t of the hull
+    float ship_off[kShipVerts];                      // ship_n[j] . ship_l[j]: offset of the hull's plane j (rotation invariant)
+    float ship_aabb[4];                                // body-frame l,b,r,t of the hull
     float goal_cull_r2;                              // (max |hull vertex| + goal radius)^2: bounding circle about the body origin
-    int fan_is_sector;                               // the 10 rays span less than pi: their box is that of a circular sector
 };
 
 struct EnvRegs {

@@ -41,10 +41,24 @@ __device__ __forceinline__ void hull_extents(const StepParams &p, float c, float
     }
 }
 
+// Reach-grid cell of the lidar origin (ox, oy): which bank edges a ray starting there can touch at all.
+__device__ __forceinline__ uint4 load_cell(const StepParams &p, int scen, float ox, float oy)
+{
+    int ix = __float2int_rd((ox - p.gridp.x0) * p.gridp.inv_cx);
+    int iy = __float2int_rd((oy - p.gridp.y0) * p.gridp.inv_cy);
+    ix = min(max(ix, 0), kGridN - 1);
+    iy = min(max(iy, 0), kGridN - 1);
+    return __ldg(p.grid + ((size_t)scen * kGridN + iy) * kGridN + ix);
+}
+
 // ------------------------------------------------------------------------------------------------------------
-// G lanes per env, 32/G envs per warp.  Scalar state is loaded once, lives in registers for K steps and is stored
-// once; the two most recent observation frames of every env -- including the sticky lidar readings, which are
-// state -- live in a padded shared-memory tile from which each step's obs rows are copied out, fully coalesced.
+// G lanes per env, 32/G envs per warp.  The lanes of a group hold identical copies of the env's scalar state
+// (loaded once, in registers for K steps, stored once).  The two most recent observation frames of every env --
+// including the sticky lidar readings, which are state -- live in a padded shared-memory tile from which each
+// step's obs rows are copied out, fully coalesced.  The irregular geometry is done by the WHOLE WARP in passes:
+//   ray pass: 3 needy envs at a time, one lane per (env, ray); the reach grid supplies the candidate edges
+//   SAT pass: 32/lps needy envs at a time, one lane per (env, bank edge), lps = 8, 16 or 32 >= max hull size
+// so that control flow stays warp-uniform no matter how few envs of a warp are near a bank.
 // ------------------------------------------------------------------------------------------------------------
 template <int G, int HIST>
 __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ StepParams p)
@@ -53,20 +67,27 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     constexpr int OBS4 = 4 * HIST;              // float4 per obs row
     constexpr int ROW4 = OBS4 + 1;              // padded tile row (odd float4 stride: conflict-free 128-bit accesses)
     constexpr int CF = 16 * (HIST - 1);         // float offset of the newest frame inside a row
-    constexpr unsigned GMASK = (G == 32) ? 0xffffffffu : ((1u << G) - 1u);
     __shared__ float4 s_tile[(kThreads / 32) * EPW * ROW4];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G, gl = lane % G;
-    const int gshift = grp * G;
     const int warp_env0 = (blockIdx.x * (kThreads / 32) + warp) * EPW;
     const int e = warp_env0 + grp;
     const bool valid = e < p.N;
     const bool leader = valid && gl == 0;
     float4 *tile = s_tile + warp * EPW * ROW4;
     float4 *row4 = tile + grp * ROW4;                               // this env's [older frame | newest frame]
-    float *lidf = reinterpret_cast<float *>(row4) + CF + 6;         // newest frame's lidar slots = the sticky vals
+    float *tile_f = reinterpret_cast<float *>(tile);
     const float L = p.lidar_len;
+
+    // lane roles in the cooperative passes
+    const int rslot = lane / kBeams;                                // ray pass: env slot 0..2 (lanes 30, 31 idle)
+    const int rj = lane - rslot * kBeams;                           // ... and ray index
+    const float ray_c = p.ray_c[rslot < 3 ? rj : 0], ray_s = p.ray_s[rslot < 3 ? rj : 0];
+    const int lps = p.maxv <= 8 ? 8 : (p.maxv <= 16 ? 16 : 32);     // SAT pass: lanes per env slot
+    const int nslots = 32 / lps;
+    const int sslot = lane / lps, sel = lane & (lps - 1);
+    const unsigned slotmask = lps == 32 ? kFull : (((1u << lps) - 1u) << (sslot * lps));
 
     float st_episodes = 0.f, st_return = 0.f, st_length = 0.f, st_goal = 0.f;
     float st_coll = 0.f, st_oob = 0.f, st_timeout = 0.f, st_allgoals = 0.f;
@@ -81,9 +102,11 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     float gx, gy;
     closest_goal(r, gx, gy);
     bool goals_dirty = false;
-    // extents of the rotated hull relative to the body origin (cached AABB of the shape)
     float hminx, hmaxx, hminy, hmaxy;
     hull_extents(p, c, s, hminx, hmaxx, hminy, hmaxy);
+    // ray origin = body origin + half the extents of the hull's cached AABB (models.py:51-53)
+    float hx = 0.5f * (hmaxx - hminx), hy = 0.5f * (hmaxy - hminy);
+    uint4 cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
     if (gl == 0) {                               // newest frame of the resident tile = frame of the current state
         row4[OBS4 - 4] = make_float4(r.x, r.y, (float)r.rudder, r.th);
         row4[OBS4 - 3] = make_float4(gx, gy, r.lid[0], r.lid[1]);
@@ -97,11 +120,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     for (int k = 0; k < p.K; ++k) {
         const int a = a_next;
         if (k + 1 < p.K) a_next = load_action(p, k + 1, valid ? e : p.N - 1, gid);    // prefetch: off the critical path
-        const float4 *rec = p.bank + (size_t)r.scen * p.scen_stride4;
-        const float4 *E0 = rec + kBankHeader4, *E1 = E0 + p.maxv;
         // previous frame <- newest frame of the last step / reset (SURVEY.md App. A note N2); lidar stays in place
         if (HIST == 2 && gl == 0) { row4[0] = row4[4]; row4[1] = row4[5]; row4[2] = row4[6]; row4[3] = row4[7]; }
-        if (HIST == 2 && G > 1) __syncwarp();      // the copy has read the old readings before any lane overwrites them
 
         // ---- ShipGame.handle_discrete_action (game.py:140-153); Ship.move_forward / rotate (models.py:129-146)
         float dvx = 0.f, dvy = 0.f, dw = 0.f;
@@ -110,132 +130,58 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
         else if (a == 2) r.rudder = min(r.rudder + 5, 10);
 
         // ---- LiDAR.query (models.py:39-76) at the PRE-integration pose (game.py:193 precedes :194)
-        // ray origin = body origin + half the extents of the hull's cached AABB (models.py:51-53)
-        const float hx = 0.5f * (hmaxx - hminx), hy = 0.5f * (hmaxy - hminy);
-        // box of the fan relative to the origin (centre fcx,fcy; half sizes fhw,fhh): sector between the first and
-        // the last ray, which contains every ray
-        float fcx, fcy, fhw, fhh;
-        {
-            float x0 = -1.f, x1 = 1.f, y0 = -1.f, y1 = 1.f;
-            if (p.fan_is_sector) {
-                const float ax = c * p.ray_c[0] - s * p.ray_s[0], ay = s * p.ray_c[0] + c * p.ray_s[0];
-                const float bx = c * p.ray_c[kBeams - 1] - s * p.ray_s[kBeams - 1], by = s * p.ray_c[kBeams - 1] + c * p.ray_s[kBeams - 1];
-                x1 = (ay <= 0.f && by >= 0.f) ? 1.f : fmaxf(0.f, fmaxf(ax, bx));
-                x0 = (ay >= 0.f && by <= 0.f) ? -1.f : fminf(0.f, fminf(ax, bx));
-                y1 = (ax >= 0.f && bx <= 0.f) ? 1.f : fmaxf(0.f, fmaxf(ay, by));
-                y0 = (ax <= 0.f && bx >= 0.f) ? -1.f : fminf(0.f, fminf(ay, by));
-            }
-            fcx = 0.5f * L * (x0 + x1); fhw = 0.5f * L * (x1 - x0) + 1e-3f;
-            fcy = 0.5f * L * (y0 + y1); fhh = 0.5f * L * (y1 - y0) + 1e-3f;
-        }
-        bool reach0, reach1;
-        {
-            const float ox = r.x + hx + fcx, oy = r.y + hy + fcy;       // fan box centre, world
-            reach0 = valid && !(ox + fhw < sc.bb0.x || ox - fhw > sc.bb0.z || oy + fhh < sc.bb0.y || oy - fhh > sc.bb0.w);
-            reach1 = valid && !(ox + fhw < sc.bb1.x || ox - fhw > sc.bb1.z || oy + fhh < sc.bb1.y || oy - fhh > sc.bb1.w);
-        }
-        // stage A (cpShapePointQuery + plane culling), edges strided over the group: is the origin inside the bank,
-        // and which planes face the origin and cut the fan box?
-        unsigned cand0 = 0u, cand1 = 0u, out0 = 0u, out1 = 0u;
-        if (G == 1) {
-            if (reach0)
-                for (int i = 0; i < sc.n0; ++i) {
-                    const float4 ed = __ldg(E0 + i);
-                    const float d = ed.x * ((r.x - ed.z) + hx) + ed.y * ((r.y - ed.w) + hy);     // n.(origin - v_i)
-                    const float dmin = d + (ed.x * fcx + ed.y * fcy) - (fabsf(ed.x) * fhw + fabsf(ed.y) * fhh);
-                    out0 |= (d > 0.f) ? 1u : 0u;
-                    cand0 |= (d >= 0.f && dmin <= 0.f) ? (1u << i) : 0u;
-                }
-            if (reach1)
-                for (int i = 0; i < sc.n1; ++i) {
-                    const float4 ed = __ldg(E1 + i);
-                    const float d = ed.x * ((r.x - ed.z) + hx) + ed.y * ((r.y - ed.w) + hy);
-                    const float dmin = d + (ed.x * fcx + ed.y * fcy) - (fabsf(ed.x) * fhw + fabsf(ed.y) * fhh);
-                    out1 |= (d > 0.f) ? 1u : 0u;
-                    cand1 |= (d >= 0.f && dmin <= 0.f) ? (1u << i) : 0u;
-                }
-        } else {
-            for (int it = 0; it * G < p.maxv; ++it) {                  // warp-uniform trip count
-                const int i = it * G + gl;
-                const bool a0 = reach0 && i < sc.n0, a1 = reach1 && i < sc.n1;
-                float d0 = -1.f, d1 = -1.f, m0 = 1.f, m1 = 1.f;
-                if (a0) {
-                    const float4 ed = __ldg(E0 + i);
-                    d0 = ed.x * ((r.x - ed.z) + hx) + ed.y * ((r.y - ed.w) + hy);
-                    m0 = d0 + (ed.x * fcx + ed.y * fcy) - (fabsf(ed.x) * fhw + fabsf(ed.y) * fhh);
-                }
-                if (a1) {
-                    const float4 ed = __ldg(E1 + i);
-                    d1 = ed.x * ((r.x - ed.z) + hx) + ed.y * ((r.y - ed.w) + hy);
-                    m1 = d1 + (ed.x * fcx + ed.y * fcy) - (fabsf(ed.x) * fhw + fabsf(ed.y) * fhh);
-                }
-                const unsigned bl0 = __ballot_sync(kFull, a0 && d0 >= 0.f && m0 <= 0.f), bo0 = __ballot_sync(kFull, a0 && d0 > 0.f);
-                const unsigned bl1 = __ballot_sync(kFull, a1 && d1 >= 0.f && m1 <= 0.f), bo1 = __ballot_sync(kFull, a1 && d1 > 0.f);
-                cand0 |= ((bl0 >> gshift) & GMASK) << (it * G); out0 |= (bo0 >> gshift) & GMASK;
-                cand1 |= ((bl1 >> gshift) & GMASK) << (it * G); out1 |= (bo1 >> gshift) & GMASK;
-            }
-        }
-        // stage B + rays, per group with the rays strided over its lanes (lane gl owns rays gl, gl+G, ...): no
-        // cross-lane traffic, hits go straight into the resident frame.  cpPolyShapeSegmentQuery: later edges
-        // overwrite earlier ones; LiDAR.query: the first bank (list order) that reports a hit wins, misses keep
-        // the old reading (sticky vals, models.py:71).
-        if ((reach0 && (out0 == 0u || cand0)) || (reach1 && (out1 == 0u || cand1))) {
-            unsigned pend = 0u;
+        unsigned need = __ballot_sync(kFull, leader && ((cell.x | cell.y | (cell.z & 3u)) != 0u));
+        if (HIST == 2) __syncwarp();            // the frame copy has read the old readings before any lane overwrites them
+        while (need) {
+            // up to three needy envs per pass: lanes 0-9 / 10-19 / 20-29 are the ten rays of slot 0 / 1 / 2
+            const int s0 = __ffs(need) - 1; need &= need - 1u;
+            int s1 = -1, s2 = -1;
+            if (need) { s1 = __ffs(need) - 1; need &= need - 1u; }
+            if (need) { s2 = __ffs(need) - 1; need &= need - 1u; }
+            const int src = rslot == 0 ? s0 : (rslot == 1 ? s1 : (rslot == 2 ? s2 : -1));
+            const bool act = src >= 0;
+            const int srcl = act ? src : lane;
+            const float bx = __shfl_sync(kFull, r.x, srcl), by = __shfl_sync(kFull, r.y, srcl);
+            const float bhx = __shfl_sync(kFull, hx, srcl), bhy = __shfl_sync(kFull, hy, srcl);
+            const float bc = __shfl_sync(kFull, c, srcl), bs = __shfl_sync(kFull, s, srcl);
+            const unsigned m0 = __shfl_sync(kFull, cell.x, srcl), m1 = __shfl_sync(kFull, cell.y, srcl);
+            const unsigned sf = __shfl_sync(kFull, (unsigned)r.scen | (cell.z << 28), srcl);
+            if (act) {
+                const int bscen = (int)(sf & 0x0fffffffu);
+                const float dirx = bc * ray_c - bs * ray_s, diry = bs * ray_c + bc * ray_s;
+                const double xd = (double)bx, yd = (double)by, hxd = (double)bhx, hyd = (double)bhy;
+                bool hit = false;
+                float val = L;
 #pragma unroll
-            for (int j = gl; j < kBeams; j += G) pend |= 1u << j;        // my rays
-#pragma unroll 1
-            for (int b = 0; b < 2; ++b) {
-                const bool rb = b == 0 ? reach0 : reach1;
-                if (!rb || pend == 0u) continue;
-                const unsigned outb = b == 0 ? out0 : out1;
-                unsigned cand = b == 0 ? cand0 : cand1;
-                const int nb = b == 0 ? sc.n0 : sc.n1;
-                const float4 *E = b == 0 ? E0 : E1;
-                if (outb == 0u) {            // start point inside the shape: alpha = 0, point stays at the ray end
-#pragma unroll
-                    for (int j = gl; j < kBeams; j += G) if (pend >> j & 1u) lidf[j] = L;
-                    pend = 0u;
-                    continue;
-                }
-                unsigned hitm = 0u;
-                while (cand) {
-                    const int i = __ffs(cand) - 1;
-                    cand &= cand - 1u;
-                    const float4 ed = __ldg(E + i);
-                    const float4 ep = __ldg(E + (i == 0 ? nb - 1 : i - 1));
-                    {   // stage B (fp32): can the fan box reach the edge's extent along the plane?
-                        const float qx = (r.x - ed.z) + hx, qy = (r.y - ed.w) + hy;
-                        const float tc = (ed.x * qy - ed.y * qx) + (ed.x * fcy - ed.y * fcx);
-                        const float te = fabsf(ed.y) * fhw + fabsf(ed.x) * fhh;
-                        const float tmin = ed.x * (ep.w - ed.w) - ed.y * (ep.z - ed.z);
-                        if (tc + te < tmin || tc - te > 0.f) continue;
-                    }
-                    // The hit distance is d / (-n.dir): an error of d is amplified by 1/cos(incidence).  The stored
-                    // fp32 normal is good to ~6e-8 rad, i.e. 6e-5 of d over a 1000-unit edge, so for live edges
-                    // the plane is rebuilt in double from the two fp32 vertices (what the reference's double
-                    // planes are made of).  FP64 runs at half the FP32 rate on B200 and few lane-steps get here.
-                    const double exd = (double)ed.z - (double)ep.z, eyd = (double)ed.w - (double)ep.w;
-                    const double len2 = exd * exd + eyd * eyd;
-                    const double inv = rsqrt(len2);
-                    const double nxd = eyd * inv, nyd = -exd * inv;
-                    const double qxd = ((double)r.x - (double)ed.z) + (double)hx;
-                    const double qyd = ((double)r.y - (double)ed.w) + (double)hy;
-                    const float d = (float)(nxd * qxd + nyd * qyd);
-                    const float ta = (float)(nxd * qyd - nyd * qxd);       // cross(n, origin - v_i)
-                    const float tmin = -(float)(len2 * inv);               // cross(n, v_{i-1} - v_i) = -|edge|
-                    const float enx = (float)nxd, eny = (float)nyd;
-                    if (d < 0.f) continue;
-#pragma unroll
-                    for (int j = gl; j < kBeams; j += G) {
-                        const float dirx = c * p.ray_c[j] - s * p.ray_s[j], diry = s * p.ray_c[j] + c * p.ray_s[j];
-                        const float denom = -L * (enx * dirx + eny * diry);    // an - bn
+                for (int b = 0; b < 2; ++b) {   // LiDAR.query: the first bank (list order) that reports a hit wins
+                    unsigned m = b ? m1 : m0;
+                    const bool maybe_in = (sf >> (28 + b)) & 1u;
+                    if (hit || (m == 0u && !maybe_in)) continue;
+                    const EdgeD *E = p.edges_d + ((size_t)bscen * 2 + b) * p.maxv;
+                    bool out = false, hb = false;
+                    float vb = L;
+                    while (m) {                 // cpPolyShapeSegmentQuery: later accepted edges overwrite earlier ones
+                        const int i = __ffs(m) - 1;
+                        m &= m - 1u;
+                        const double2 nd = __ldg(reinterpret_cast<const double2 *>(E + i));
+                        const float4 ev = __ldg(reinterpret_cast<const float4 *>(E + i) + 1);
+                        const double qx = (xd - (double)ev.x) + hxd, qy = (yd - (double)ev.y) + hyd;     // origin - v_i
+                        const float d = (float)(nd.x * qx + nd.y * qy);
+                        const float ta = (float)(nd.x * qy - nd.y * qx);                                   // cross(n, origin - v_i)
+                        const float enx = (float)nd.x, eny = (float)nd.y;
+                        out = out || (d > 0.f);
+                        const float denom = -L * (enx * dirx + eny * diry);                                // an - bn
                         float t;
-                        if (denom > 0.f) t = __fdividef(d, denom); else t = (d == 0.f) ? 0.f : 2.f;   // d / max(an-bn, DBL_MIN)
-                        const float tang = ta + t * L * (enx * diry - eny * dirx);                  // cross(n, hit - v_i)
-                        if ((pend >> j & 1u) && (t <= 1.f) && (tang >= tmin) && (tang <= 0.f)) { lidf[j] = t * L; hitm |= 1u << j; }
+                        if (denom > 0.f) t = __fdividef(d, denom); else t = (d == 0.f) ? 0.f : 2.f;       // d / max(an-bn, DBL_MIN)
+                        const float tang = ta + t * L * (enx * diry - eny * dirx);                         // cross(n, hit - v_i)
+                        if (d >= 0.f && t <= 1.f && tang >= -ev.z && tang <= 0.f) { vb = t * L; hb = true; }
                     }
+                    // cpShapeSegmentQuery: start point inside the shape => alpha = 0 and `point` stays at the ray end
+                    if (maybe_in && !out) { vb = L; hb = true; }
+                    if (hb) { hit = true; val = vb; }
                 }
-                pend &= ~hitm;
+                // misses keep the old reading (sticky vals, models.py:71)
+                if (hit) tile_f[(src / G) * (ROW4 * 4) + CF + 6 + rj] = val;
             }
         }
 
@@ -245,6 +191,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
         r.th += r.w * p.dt;
         sincos_fast(r.th, s, c);
         hull_extents(p, c, s, hminx, hmaxx, hminy, hmaxy);
+        hx = 0.5f * (hmaxx - hminx); hy = 0.5f * (hmaxy - hminy);
+        cell = load_cell(p, r.scen, r.x + hx, r.y + hy);          // for the NEXT step's lidar; consumed a whole step later
 
         // ---- overlap tests at the new pose -> begin callbacks collide_ship / collide_goal (game.py:232-257)
         // cpBBIntersects (inclusive) pre-filter of the narrow phase
@@ -252,16 +200,26 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
         const bool ov1 = valid && !(r.x + hminx > sc.bb1.z || r.x + hmaxx < sc.bb1.x || r.y + hminy > sc.bb1.w || r.y + hmaxy < sc.bb1.y);
         bool colliding = false;
         {
-            // cooperative separating-axis test: lanes <-> bank edges (n <= 32).  Contact <=> no separating axis
-            // among the edge normals of both convex polygons (touching counts: GJK distance <= 0).
-            unsigned needy = __ballot_sync(kFull, gl == 0 && (ov0 || ov1));
-            while (needy) {
-                const int src = __ffs(needy) - 1;
-                needy &= needy - 1u;
-                const float bx = __shfl_sync(kFull, r.x, src), by = __shfl_sync(kFull, r.y, src);
-                const float bc = __shfl_sync(kFull, c, src), bs = __shfl_sync(kFull, s, src);
-                const int bscen = __shfl_sync(kFull, r.scen, src);
-                const int bflags = __shfl_sync(kFull, sc.n0 | (sc.n1 << 8) | ((int)ov0 << 16) | ((int)ov1 << 17), src);
+            // cooperative separating-axis test, nslots envs per pass, lanes <-> bank edges.  Contact <=> no separating
+            // axis among the edge normals of both convex polygons (touching counts: GJK distance <= 0).
+            unsigned needs = __ballot_sync(kFull, gl == 0 && (ov0 || ov1));
+            while (needs) {
+                int src = -1, myslot = -1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < nslots && needs) {
+                        const int t = __ffs(needs) - 1;
+                        needs &= needs - 1u;
+                        if (sslot == q) src = t;
+                        if (t / G == grp) myslot = q;
+                    }
+                }
+                const bool act_env = src >= 0;
+                const int srcl = act_env ? src : lane;
+                const float bx = __shfl_sync(kFull, r.x, srcl), by = __shfl_sync(kFull, r.y, srcl);
+                const float bc = __shfl_sync(kFull, c, srcl), bs = __shfl_sync(kFull, s, srcl);
+                const int bscen = __shfl_sync(kFull, r.scen, srcl);
+                const int bflags = __shfl_sync(kFull, sc.n0 | (sc.n1 << 8) | ((int)ov0 << 16) | ((int)ov1 << 17), srcl);
                 const float4 *bE = p.bank + (size_t)bscen * p.scen_stride4 + kBankHeader4;
                 float rx[kShipVerts], ry[kShipVerts];
 #pragma unroll
@@ -272,31 +230,31 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                 bool coll = false;
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
-                    if (((bflags >> (16 + b)) & 1) && !coll) {
-                        const int nb = (bflags >> (8 * b)) & 0xff;
-                        const bool act = lane < nb;
-                        float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (act) ed = __ldg(bE + b * p.maxv + lane);
-                        float m = ed.x * rx[0] + ed.y * ry[0];
+                    const bool do_b = act_env && ((bflags >> (16 + b)) & 1) && !coll;
+                    const int nb = (bflags >> (8 * b)) & 0xff;
+                    const bool actl = do_b && sel < nb;
+                    float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (actl) ed = __ldg(bE + b * p.maxv + sel);
+                    float m = ed.x * rx[0] + ed.y * ry[0];
 #pragma unroll
-                        for (int j = 1; j < kShipVerts; ++j) m = fminf(m, ed.x * rx[j] + ed.y * ry[j]);
-                        const float base = ed.x * (bx - ed.z) + ed.y * (by - ed.w);
-                        bool sep = __ballot_sync(kFull, act && base + m > 0.f) != 0u;      // a bank edge normal separates
-                        if (!sep) {
+                    for (int j = 1; j < kShipVerts; ++j) m = fminf(m, ed.x * rx[j] + ed.y * ry[j]);
+                    const float base = ed.x * (bx - ed.z) + ed.y * (by - ed.w);
+                    const unsigned sb = __ballot_sync(kFull, actl && base + m > 0.f);      // a bank edge normal separates
+                    bool sep = (sb & slotmask) != 0u;
+                    if (__ballot_sync(kFull, do_b && !sep)) {                               // rare: try the ship's edge normals
 #pragma unroll
-                            for (int j = 0; j < kShipVerts; ++j) {                          // ship edge normals
-                                const float nx = p.ship_nx[j] * bc - p.ship_ny[j] * bs;
-                                const float ny = p.ship_nx[j] * bs + p.ship_ny[j] * bc;
-                                const float off = nx * rx[j] + ny * ry[j];
-                                const float pr = act ? nx * (ed.z - bx) + ny * (ed.w - by) : 3.0e38f;
-                                const int mn = __reduce_min_sync(kFull, f2ord(pr));
-                                sep = sep || (mn > f2ord(off));
-                            }
+                        for (int j = 0; j < kShipVerts; ++j) {
+                            const float nx = p.ship_nx[j] * bc - p.ship_ny[j] * bs;
+                            const float ny = p.ship_nx[j] * bs + p.ship_ny[j] * bc;
+                            const float pr = actl ? nx * (ed.z - bx) + ny * (ed.w - by) : 3.0e38f;
+                            const int mn = __reduce_min_sync(slotmask, f2ord(pr));
+                            sep = sep || (mn > f2ord(p.ship_off[j]));
                         }
-                        coll = !sep;
                     }
+                    if (do_b && !sep) coll = true;
                 }
-                if (coll && (lane / G) == (src / G)) colliding = true;
+                const unsigned res = __ballot_sync(kFull, coll);
+                if (myslot >= 0 && ((res >> (myslot * lps)) & 1u)) colliding = true;
             }
         }
         bool goal_reached = false;
@@ -358,6 +316,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                 load_scen_consts(p, r.scen, sc);
                 c = 1.f; s = 0.f;
                 hminx = p.ship_aabb[0]; hminy = p.ship_aabb[1]; hmaxx = p.ship_aabb[2]; hmaxy = p.ship_aabb[3];
+                hx = 0.5f * (hmaxx - hminx); hy = 0.5f * (hmaxy - hminy);
+                cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
                 closest_goal(r, gx, gy);
                 goals_dirty = true;
             }
@@ -416,6 +376,88 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
         for (int i = 0; i < 8; ++i)
             if (v[i] != 0.f) atomicAdd(srow + i, (double)v[i]);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// reach-grid build kernel: one thread per (scenario, cell), double precision.  Runs once per scenario upload.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double point_rect_dist(double px, double py, double x0, double y0, double x1, double y1)
+{
+    const double dx = fmax(fmax(x0 - px, px - x1), 0.0), dy = fmax(fmax(y0 - py, py - y1), 0.0);
+    return sqrt(dx * dx + dy * dy);
+}
+
+__device__ __forceinline__ double point_seg_dist(double px, double py, double ax, double ay, double bx, double by)
+{
+    const double ex = bx - ax, ey = by - ay;
+    const double den = ex * ex + ey * ey;
+    double t = den > 0.0 ? ((px - ax) * ex + (py - ay) * ey) / den : 0.0;
+    t = fmin(fmax(t, 0.0), 1.0);
+    const double dx = px - (ax + t * ex), dy = py - (ay + t * ey);
+    return sqrt(dx * dx + dy * dy);
+}
+
+// distance between the segment a-b and the axis-aligned rectangle [x0,x1] x [y0,y1] (0 when they intersect)
+__device__ double seg_rect_dist(double ax, double ay, double bx, double by, double x0, double y0, double x1, double y1)
+{
+    {   // Liang-Barsky: does any part of the segment lie inside the rectangle?
+        double t0 = 0.0, t1 = 1.0;
+        const double dx = bx - ax, dy = by - ay;
+        const double pp[4] = {-dx, dx, -dy, dy};
+        const double qq[4] = {ax - x0, x1 - ax, ay - y0, y1 - ay};
+        bool inside = true;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (pp[i] == 0.0) { if (qq[i] < 0.0) inside = false; }
+            else {
+                const double t = qq[i] / pp[i];
+                if (pp[i] < 0.0) t0 = fmax(t0, t); else t1 = fmin(t1, t);
+            }
+        }
+        if (inside && t0 <= t1) return 0.0;
+    }
+    double d = fmin(point_rect_dist(ax, ay, x0, y0, x1, y1), point_rect_dist(bx, by, x0, y0, x1, y1));
+    d = fmin(d, point_seg_dist(x0, y0, ax, ay, bx, by));
+    d = fmin(d, point_seg_dist(x1, y0, ax, ay, bx, by));
+    d = fmin(d, point_seg_dist(x0, y1, ax, ay, bx, by));
+    d = fmin(d, point_seg_dist(x1, y1, ax, ay, bx, by));
+    return d;
+}
+
+__global__ void __launch_bounds__(256) build_grid_kernel(const double *hull_xy, const int *hull_n, int n_scen, int maxv_in,
+                                                         double gx0, double gy0, double cw, double ch, double reach,
+                                                         double touch_margin, uint4 *grid)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)n_scen * kGridN * kGridN) return;
+    const int s = (int)(t / (kGridN * kGridN)), cidx = (int)(t % (kGridN * kGridN));
+    const int ix = cidx % kGridN, iy = cidx / kGridN;
+    const double kBig = 1.0e12;
+    const bool border = ix == 0 || iy == 0 || ix == kGridN - 1 || iy == kGridN - 1;
+    const double x0 = ix == 0 ? -kBig : gx0 + ix * cw, x1 = ix == kGridN - 1 ? kBig : gx0 + (ix + 1) * cw;
+    const double y0 = iy == 0 ? -kBig : gy0 + iy * ch, y1 = iy == kGridN - 1 ? kBig : gy0 + (iy + 1) * ch;
+    // a finite point of the cell (used when no edge comes near: the cell is then entirely inside or outside)
+    const double px = ix == 0 ? x1 : x0, py = iy == 0 ? y1 : y0;
+    unsigned masks[2] = {0u, 0u}, flags = 0u;
+    for (int b = 0; b < 2; ++b) {
+        const double *v = hull_xy + ((size_t)s * 2 + b) * maxv_in * 2;
+        const int n = hull_n[s * 2 + b];
+        bool touch = false, pin = true;
+        for (int i = 0; i < n; ++i) {
+            const int j = i == 0 ? n - 1 : i - 1;
+            const double ax = v[2 * j], ay = v[2 * j + 1], bx = v[2 * i], by = v[2 * i + 1];
+            const double d = seg_rect_dist(ax, ay, bx, by, x0, y0, x1, y1);
+            if (d <= reach) masks[b] |= 1u << i;
+            if (d <= touch_margin) touch = true;
+            // outward normal of a CCW loop is (ey, -ex): p is inside iff it is behind every plane
+            if ((by - ay) * (px - bx) - (bx - ax) * (py - by) > 0.0) pin = false;
+        }
+        if (touch || pin) {
+            flags |= 1u << b;
+            if (border) masks[b] = n >= 32 ? kFull : ((1u << n) - 1u);      // unbounded cell: the inside test needs every plane
+        }
+    }
+    grid[t] = make_uint4(masks[0], masks[1], flags, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -492,6 +534,15 @@ cudaError_t launch_reset(const StepParams &p, const uint8_t *mask, const int *sc
 {
     const int threads = 256;
     reset_kernel<<<(p.N + threads - 1) / threads, threads, 0, stream>>>(p, mask, scenario, first, obs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_grid(const double *hull_xy, const int *hull_n, int n_scen, int maxv_in, double gx0, double gy0,
+                              double cw, double ch, double reach, double touch_margin, uint4 *grid, cudaStream_t stream)
+{
+    const long long total = (long long)n_scen * kGridN * kGridN;
+    build_grid_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(hull_xy, hull_n, n_scen, maxv_in, gx0, gy0, cw, ch,
+                                                                          reach, touch_margin, grid);
     return cudaGetLastError();
 }
 

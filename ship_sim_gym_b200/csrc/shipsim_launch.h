@@ -13,6 +13,8 @@ struct LaunchShape { int lanes_per_env, threads, blocks; };
 cudaError_t launch_step(const StepParams &p, int lanes_per_env, cudaStream_t stream, LaunchShape *shape);
 cudaError_t launch_reset(const StepParams &p, const uint8_t *mask, const int *scenario, int first, float4 *obs,
                          cudaStream_t stream);
+cudaError_t launch_build_grid(const double *hull_xy, const int *hull_n, int n_scen, int maxv_in, double gx0, double gy0,
+                              double cw, double ch, double reach, double touch_margin, uint4 *grid, cudaStream_t stream);
 cudaError_t launch_stats_reduce(double *slots, double *out, int clear, cudaStream_t stream);
 
 }  // namespace shipsim
