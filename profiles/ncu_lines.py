@@ -69,6 +69,13 @@ print("%7s %7s %6s  %s" % ("inst%", "smp%", "lanes", "location"))
 for loc, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
     print("%6.2f%% %6.2f%% %6.1f  %s:%d  %s" % (100 * a[0] / tot_i, 100 * a[1] / tot_s, a[2] / max(a[0], 1), loc[0], loc[1], src(loc)))
 
+if len(sys.argv) > 3:      # full listing in source order, instructions per `norm` (e.g. warp-steps per launch)
+    norm = float(sys.argv[3])
+    print("\nsource order: warp-instructions per unit (norm %g), stall samples %%, avg active lanes" % norm)
+    for loc, a in sorted(agg.items()):
+        if a[0] / norm >= 0.5:
+            print("%8.1f %6.2f%% %6.1f  %s:%d  %s" % (a[0] / norm, 100 * a[1] / tot_s, a[2] / max(a[0], 1), loc[0], loc[1], src(loc)))
+
 # ---- coarse regions of shipsim_kernels.cu (by marker comments) + device header
 import bisect
 ksrc = open(os.path.join(ROOT, "ship_sim_gym_b200", "csrc", "shipsim_kernels.cu")).read().splitlines()

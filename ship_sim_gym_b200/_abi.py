@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libshipsim.so")
+LIB_PATH = os.environ.get("SHIPSIM_LIB") or os.path.join(HERE, "libshipsim.so")   # override: kernel-variant experiments
 
 ACTION_I32, ACTION_I64, ACTION_U8, ACTION_RANDOM = 0, 1, 2, 3
 STATS_LEN = 16

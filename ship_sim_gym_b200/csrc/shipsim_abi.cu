@@ -226,7 +226,7 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
     }
     const int stride4 = kBankHeader4 + 2 * dev_maxv;
     std::vector<float4> host((size_t)n_scen * stride4, make_float4(0.f, 0.f, 0.f, 0.f));
-    std::vector<EdgeD> edges((size_t)n_scen * 2 * dev_maxv);
+    std::vector<EdgeD> edges((size_t)n_scen * 2 * kMaxHull);
     std::memset(edges.data(), 0, edges.size() * sizeof(EdgeD));
     // the device geometry is the fp32-rounded polygon: every derived quantity (fp32 planes, double planes, reach
     // grid) is computed in double from the ROUNDED vertices, so the representations agree with each other
@@ -247,7 +247,7 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
             if (!(area2 > 0)) return fail(SHIPSIM_ERR_ARG, "bank hulls must be convex and counter-clockwise");
             rec[b] = make_float4(round_down(l), round_down(bo), round_up(r), round_up(t));
             float4 *E = rec + kBankHeader4 + b * dev_maxv;
-            EdgeD *ED = edges.data() + ((size_t)s * 2 + b) * dev_maxv;
+            EdgeD *ED = edges.data() + ((size_t)s * 2 + b) * kMaxHull;
             for (int i = 0; i < n; ++i) {
                 const double ax = v[2 * ((i + n - 1) % n)], ay = v[2 * ((i + n - 1) % n) + 1], bx = v[2 * i], by = v[2 * i + 1];
                 const double ex = bx - ax, ey = by - ay, ln = std::sqrt(ex * ex + ey * ey);

@@ -25,6 +25,7 @@ constexpr int kShipVerts = 5;
 constexpr int kStatSlots = 128;     // replicated accumulator rows (one 128-byte line each) to spread atomics
 constexpr int kStatLen = 16;
 constexpr int kBankHeader4 = 6;     // float4s before the edge records of a scenario
+constexpr int kMaxHull = 32;        // SHIPSIM_MAX_HULL: fixed stride of the double-plane records
 constexpr int kGridN = 32;          // the reach grid has kGridN x kGridN cells per scenario
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -59,7 +60,7 @@ struct GridParams {
 struct StepParams {
     float4 *state;               // [kPlanes][N]
     const float4 *bank;          // packed scenario records
-    const EdgeD *edges_d;        // [n_scen][2][maxv] double planes
+    const EdgeD *edges_d;        // [n_scen][2][kMaxHull] double planes
     const uint4 *grid;           // [n_scen][kGridN*kGridN] reach grid
     GridParams gridp;
     const void *actions;         // [K][N]
@@ -241,6 +242,8 @@ __device__ __forceinline__ bool goal_touches_ship(const StepParams &p, float qx,
     }
     return !outside || best <= p.goal_r * p.goal_r;
 }
+
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
 // order-preserving float <-> int map for __reduce_min_sync
 __device__ __forceinline__ int f2ord(float f) { const int k = __float_as_int(f); return k ^ ((k >> 31) & 0x7fffffff); }

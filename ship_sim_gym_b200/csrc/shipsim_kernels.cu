@@ -4,17 +4,33 @@
 #include "shipsim_device.cuh"
 #include "shipsim_launch.h"
 
+#ifndef SHIPSIM_MIN_BLOCKS
+#define SHIPSIM_MIN_BLOCKS 4
+#endif
+
 namespace shipsim {
 
-__device__ __forceinline__ int load_action(const StepParams &p, int k, int e, long long gid)
+// actions[k][e]: `ap` walks down this env's column (stride = one row of the action tensor, in bytes)
+__device__ __forceinline__ int load_action(const StepParams &p, const char *ap, int k, long long gid)
 {
-    const size_t idx = (size_t)k * p.N + e;
     switch (p.action_dtype) {
-        case 0: return __ldg(reinterpret_cast<const int *>(p.actions) + idx);
-        case 1: return (int)__ldg(reinterpret_cast<const long long *>(p.actions) + idx);
-        case 2: return (int)__ldg(reinterpret_cast<const unsigned char *>(p.actions) + idx);
+        case 0: return __ldg(reinterpret_cast<const int *>(ap));
+        case 1: return (int)__ldg(reinterpret_cast<const long long *>(ap));
+        case 2: return (int)__ldg(reinterpret_cast<const unsigned char *>(ap));
         default: return random_action(p, gid, p.step0 + (unsigned)k);
     }
+}
+
+// One bank-normal axis of the separating-axis test: does plane `ed` of the bank have the whole ship (rotated hull
+// rx/ry about the body origin bx/by) strictly in front of it?  Explicit fma/mul so that every call site rounds alike.
+__device__ __forceinline__ bool bank_axis_separates(const float4 ed, const float (&rx)[kShipVerts], const float (&ry)[kShipVerts],
+                                                    float bx, float by)
+{
+    float m = fmaf(ed.x, rx[0], __fmul_rn(ed.y, ry[0]));
+#pragma unroll
+    for (int j = 1; j < kShipVerts; ++j) m = fminf(m, fmaf(ed.x, rx[j], __fmul_rn(ed.y, ry[j])));
+    const float base = fmaf(ed.x, bx - ed.z, __fmul_rn(ed.y, by - ed.w));
+    return base + m > 0.f;
 }
 
 struct ScenConsts { float4 bb0, bb1; int n0, n1; };
@@ -51,6 +67,74 @@ __device__ __forceinline__ uint4 load_cell(const StepParams &p, int scen, float 
     return __ldg(p.grid + ((size_t)scen * kGridN + iy) * kGridN + ix);
 }
 
+constexpr int kMaxCand = 4;          // candidate planes per env the shared-memory scratch holds (more -> serial path)
+
+// A candidate plane seen from the ray origin (ox, oy) = (x + hx, y + hy), evaluated in double from the plane the
+// reference's cpSplittingPlane holds: d = n.(o - v_i), ta = cross(n, o - v_i); n is returned scaled by -L so that
+// the per-ray part needs no further multiplies.
+struct PlaneEval { float d, ta, nxl, nyl, len; };
+
+__device__ __forceinline__ PlaneEval eval_plane(const EdgeD *E, double xd, double yd, double hxd, double hyd, float L)
+{
+    const double2 nd = __ldg(reinterpret_cast<const double2 *>(E));
+    const float4 ev = __ldg(reinterpret_cast<const float4 *>(E) + 1);
+    const double qx = (xd - (double)ev.x) + hxd, qy = (yd - (double)ev.y) + hyd;     // origin - v_i
+    PlaneEval o;
+    o.d = (float)(nd.x * qx + nd.y * qy);
+    o.ta = (float)(nd.x * qy - nd.y * qx);
+    o.nxl = -L * (float)nd.x;
+    o.nyl = -L * (float)nd.y;
+    o.len = ev.z;
+    return o;
+}
+
+// One ray against one candidate plane (cpPolyShapeSegmentQuery's loop body).  t = d / max(an - bn, DBL_MIN) and the
+// test t <= 1 is evaluated as d <= an - bn; `hit` <=> the reference accepts this edge, `val` = |hit - origin|.
+__device__ __forceinline__ bool ray_vs_plane(const PlaneEval &e, float dirx, float diry, float L, float &val)
+{
+    const float denom = e.nxl * dirx + e.nyl * diry;                      // an - bn
+    const float cr = e.nxl * diry - e.nyl * dirx;                         // -L * cross(n, dir)
+    const bool pos = denom > 0.f;
+    const float t = pos ? __fdividef(e.d, denom) : 0.f;
+    const float tang = e.ta - t * cr;                                     // cross(n, hit - v_i)
+    val = t * L;
+    return e.d >= 0.f && (pos ? e.d <= denom : e.d == 0.f) && tang >= -e.len && tang <= 0.f;
+}
+
+// Serial LiDAR.query of one env by one lane: only for cells with more than kMaxCand candidate planes.
+__device__ __noinline__ void ray_query_serial(const StepParams &p, float x, float y, float hx, float hy, float c, float s, int scen,
+                                              unsigned m0, unsigned m1, unsigned flags, float *lid)
+{
+    const float L = p.lidar_len;
+    const EdgeD *E = p.edges_d + (size_t)scen * (2 * kMaxHull);
+    const double xd = (double)x, yd = (double)y, hxd = (double)hx, hyd = (double)hy;
+    unsigned pend = (1u << kBeams) - 1u;
+    for (int b = 0; b < 2; ++b) {
+        const unsigned mb = b ? m1 : m0;
+        bool out = false;
+        unsigned hitm = 0u;
+        float v[kBeams];
+        for (unsigned m = mb; m; m &= m - 1u) {
+            const PlaneEval pe = eval_plane(E + b * kMaxHull + (__ffs(m) - 1), xd, yd, hxd, hyd, L);
+            out = out || (pe.d > 0.f);
+#pragma unroll
+            for (int j = 0; j < kBeams; ++j) {
+                const float dirx = c * p.ray_c[j] - s * p.ray_s[j], diry = s * p.ray_c[j] + c * p.ray_s[j];
+                float val;
+                if (ray_vs_plane(pe, dirx, diry, L, val)) { v[j] = val; hitm |= 1u << j; }
+            }
+        }
+        const bool inside = ((flags >> b) & 1u) && !out;
+#pragma unroll
+        for (int j = 0; j < kBeams; ++j)
+            if ((pend >> j) & 1u) {
+                if (inside) lid[j] = L;
+                else if ((hitm >> j) & 1u) lid[j] = v[j];
+            }
+        pend &= inside ? 0u : ~hitm;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // G lanes per env, 32/G envs per warp.  The lanes of a group hold identical copies of the env's scalar state
 // (loaded once, in registers for K steps, stored once).  The two most recent observation frames of every env --
@@ -61,13 +145,17 @@ __device__ __forceinline__ uint4 load_cell(const StepParams &p, int scen, float 
 // so that control flow stays warp-uniform no matter how few envs of a warp are near a bank.
 // ------------------------------------------------------------------------------------------------------------
 template <int G, int HIST>
-__global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ StepParams p)
+__global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int EPW = 32 / G;                 // envs per warp
     constexpr int OBS4 = 4 * HIST;              // float4 per obs row
     constexpr int ROW4 = OBS4 + 1;              // padded tile row (odd float4 stride: conflict-free 128-bit accesses)
     constexpr int CF = 16 * (HIST - 1);         // float offset of the newest frame inside a row
+    constexpr int SCR4 = 1 + 2 * kMaxCand;      // scratch row: header + two float4 per candidate plane (odd stride)
     __shared__ float4 s_tile[(kThreads / 32) * EPW * ROW4];
+    __shared__ float4 s_scr[(kThreads / 32) * EPW * SCR4];
+
+    __shared__ float s_ray[2 * 32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int grp = lane / G, gl = lane % G;
@@ -78,16 +166,23 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     float4 *tile = s_tile + warp * EPW * ROW4;
     float4 *row4 = tile + grp * ROW4;                               // this env's [older frame | newest frame]
     float *tile_f = reinterpret_cast<float *>(tile);
+    float4 *scr = s_scr + warp * EPW * SCR4;
     const float L = p.lidar_len;
 
     // lane roles in the cooperative passes
     const int rslot = lane / kBeams;                                // ray pass: env slot 0..2 (lanes 30, 31 idle)
-    const int rj = lane - rslot * kBeams;                           // ... and ray index
-    const float ray_c = p.ray_c[rslot < 3 ? rj : 0], ray_s = p.ray_s[rslot < 3 ? rj : 0];
-    const int lps = p.maxv <= 8 ? 8 : (p.maxv <= 16 ? 16 : 32);     // SAT pass: lanes per env slot
-    const int nslots = 32 / lps;
-    const int sslot = lane / lps, sel = lane & (lps - 1);
+    if (threadIdx.x < 32) {                                         // per-lane ray direction table (body frame)
+        const int j = threadIdx.x % kBeams;
+        s_ray[threadIdx.x] = p.ray_c[j];
+        s_ray[32 + threadIdx.x] = p.ray_s[j];
+    }
+    const int lps_sh = p.maxv <= 8 ? 3 : (p.maxv <= 16 ? 4 : 5);    // SAT pass: log2(lanes per env slot)
+    const int lps = 1 << lps_sh, nslots = 32 >> lps_sh;
+    const int sslot = lane >> lps_sh, sel = lane & (lps - 1);
     const unsigned slotmask = lps == 32 ? kFull : (((1u << lps) - 1u) << (sslot * lps));
+
+    const int cp_row0 = lane / OBS4, cp_src0 = cp_row0 * ROW4 + lane % OBS4;      // obs copy-out: this lane's first float4
+    const int n_rows = min(EPW, p.N - warp_env0);
 
     float st_episodes = 0.f, st_return = 0.f, st_length = 0.f, st_goal = 0.f;
     float st_coll = 0.f, st_oob = 0.f, st_timeout = 0.f, st_allgoals = 0.f;
@@ -107,19 +202,24 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
     // ray origin = body origin + half the extents of the hull's cached AABB (models.py:51-53)
     float hx = 0.5f * (hmaxx - hminx), hy = 0.5f * (hmaxy - hminy);
     uint4 cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
+    int axis0 = 0, axis1 = 0;                    // last separating bank edge per bank (temporal coherence; never stored)
     if (gl == 0) {                               // newest frame of the resident tile = frame of the current state
         row4[OBS4 - 4] = make_float4(r.x, r.y, (float)r.rudder, r.th);
         row4[OBS4 - 3] = make_float4(gx, gy, r.lid[0], r.lid[1]);
         row4[OBS4 - 2] = make_float4(r.lid[2], r.lid[3], r.lid[4], r.lid[5]);
         row4[OBS4 - 1] = make_float4(r.lid[6], r.lid[7], r.lid[8], r.lid[9]);
     }
-    int a_next = load_action(p, 0, valid ? e : p.N - 1, gid);
-    __syncwarp();
+    const size_t act_esize = p.action_dtype == 1 ? 8 : (p.action_dtype == 2 ? 1 : 4);
+    const size_t act_stride = (size_t)p.N * act_esize;
+    const char *ap = reinterpret_cast<const char *>(p.actions) + (size_t)(valid ? e : p.N - 1) * act_esize;
+    int a_next = load_action(p, ap, 0, gid);
+    __syncthreads();                             // s_ray visible; also orders the tile initialisation
 
 #pragma unroll 1
     for (int k = 0; k < p.K; ++k) {
         const int a = a_next;
-        if (k + 1 < p.K) a_next = load_action(p, k + 1, valid ? e : p.N - 1, gid);    // prefetch: off the critical path
+        ap += act_stride;
+        if (k + 1 < p.K) a_next = load_action(p, ap, k + 1, gid);                     // prefetch: off the critical path
         // previous frame <- newest frame of the last step / reset (SURVEY.md App. A note N2); lidar stays in place
         if (HIST == 2 && gl == 0) { row4[0] = row4[4]; row4[1] = row4[5]; row4[2] = row4[6]; row4[3] = row4[7]; }
 
@@ -130,58 +230,69 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
         else if (a == 2) r.rudder = min(r.rudder + 5, 10);
 
         // ---- LiDAR.query (models.py:39-76) at the PRE-integration pose (game.py:193 precedes :194)
-        unsigned need = __ballot_sync(kFull, leader && ((cell.x | cell.y | (cell.z & 3u)) != 0u));
+        // phase 1, per env (owner lane): evaluate the candidate planes the reach grid names, in double, into the scratch row
+        const bool needy = leader && ((cell.x | cell.y | (cell.z & 3u)) != 0u);
+        const bool big = needy && (__popc(cell.x) + __popc(cell.y) > kMaxCand);
         if (HIST == 2) __syncwarp();            // the frame copy has read the old readings before any lane overwrites them
-        while (need) {
-            // up to three needy envs per pass: lanes 0-9 / 10-19 / 20-29 are the ten rays of slot 0 / 1 / 2
-            const int s0 = __ffs(need) - 1; need &= need - 1u;
-            int s1 = -1, s2 = -1;
-            if (need) { s1 = __ffs(need) - 1; need &= need - 1u; }
-            if (need) { s2 = __ffs(need) - 1; need &= need - 1u; }
-            const int src = rslot == 0 ? s0 : (rslot == 1 ? s1 : (rslot == 2 ? s2 : -1));
-            const bool act = src >= 0;
-            const int srcl = act ? src : lane;
-            const float bx = __shfl_sync(kFull, r.x, srcl), by = __shfl_sync(kFull, r.y, srcl);
-            const float bhx = __shfl_sync(kFull, hx, srcl), bhy = __shfl_sync(kFull, hy, srcl);
-            const float bc = __shfl_sync(kFull, c, srcl), bs = __shfl_sync(kFull, s, srcl);
-            const unsigned m0 = __shfl_sync(kFull, cell.x, srcl), m1 = __shfl_sync(kFull, cell.y, srcl);
-            const unsigned sf = __shfl_sync(kFull, (unsigned)r.scen | (cell.z << 28), srcl);
-            if (act) {
-                const int bscen = (int)(sf & 0x0fffffffu);
-                const float dirx = bc * ray_c - bs * ray_s, diry = bs * ray_c + bc * ray_s;
-                const double xd = (double)bx, yd = (double)by, hxd = (double)bhx, hyd = (double)bhy;
-                bool hit = false;
-                float val = L;
-#pragma unroll
-                for (int b = 0; b < 2; ++b) {   // LiDAR.query: the first bank (list order) that reports a hit wins
-                    unsigned m = b ? m1 : m0;
-                    const bool maybe_in = (sf >> (28 + b)) & 1u;
-                    if (hit || (m == 0u && !maybe_in)) continue;
-                    const EdgeD *E = p.edges_d + ((size_t)bscen * 2 + b) * p.maxv;
-                    bool out = false, hb = false;
-                    float vb = L;
-                    while (m) {                 // cpPolyShapeSegmentQuery: later accepted edges overwrite earlier ones
-                        const int i = __ffs(m) - 1;
-                        m &= m - 1u;
-                        const double2 nd = __ldg(reinterpret_cast<const double2 *>(E + i));
-                        const float4 ev = __ldg(reinterpret_cast<const float4 *>(E + i) + 1);
-                        const double qx = (xd - (double)ev.x) + hxd, qy = (yd - (double)ev.y) + hyd;     // origin - v_i
-                        const float d = (float)(nd.x * qx + nd.y * qy);
-                        const float ta = (float)(nd.x * qy - nd.y * qx);                                   // cross(n, origin - v_i)
-                        const float enx = (float)nd.x, eny = (float)nd.y;
-                        out = out || (d > 0.f);
-                        const float denom = -L * (enx * dirx + eny * diry);                                // an - bn
-                        float t;
-                        if (denom > 0.f) t = __fdividef(d, denom); else t = (d == 0.f) ? 0.f : 2.f;       // d / max(an-bn, DBL_MIN)
-                        const float tang = ta + t * L * (enx * diry - eny * dirx);                         // cross(n, hit - v_i)
-                        if (d >= 0.f && t <= 1.f && tang >= -ev.z && tang <= 0.f) { vb = t * L; hb = true; }
-                    }
-                    // cpShapeSegmentQuery: start point inside the shape => alpha = 0 and `point` stays at the ray end
-                    if (maybe_in && !out) { vb = L; hb = true; }
-                    if (hb) { hit = true; val = vb; }
+        if (needy) {
+            if (big) {
+                ray_query_serial(p, r.x, r.y, hx, hy, c, s, r.scen, cell.x, cell.y, cell.z, tile_f + grp * (ROW4 * 4) + CF + 6);
+            } else {
+                float4 *row = scr + grp * SCR4;
+                const EdgeD *E = p.edges_d + (size_t)r.scen * (2 * kMaxHull);
+                const double xd = (double)r.x, yd = (double)r.y, hxd = (double)hx, hyd = (double)hy;
+                unsigned m0 = cell.x, m1 = cell.y;
+                int n = 0;
+                bool out0 = false, out1 = false;
+                while (m0 | m1) {
+                    int idx;
+                    if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
+                    const PlaneEval pe = eval_plane(E + idx, xd, yd, hxd, hyd, L);
+                    if (idx < kMaxHull) out0 = out0 || (pe.d > 0.f); else out1 = out1 || (pe.d > 0.f);
+                    row[1 + 2 * n] = make_float4(pe.d, pe.ta, pe.nxl, pe.nyl);
+                    row[2 + 2 * n] = make_float4(pe.len, idx < kMaxHull ? 0.f : 1.f, 0.f, 0.f);
+                    ++n;
                 }
-                // misses keep the old reading (sticky vals, models.py:71)
-                if (hit) tile_f[(src / G) * (ROW4 * 4) + CF + 6 + rj] = val;
+                // cpShapeSegmentQuery: start point inside the shape => alpha = 0 and `point` stays at the ray end
+                const unsigned in0 = ((cell.z & 1u) && !out0) ? 1u : 0u, in1 = ((cell.z & 2u) && !out1) ? 1u : 0u;
+                row[0] = make_float4(c, s, __int_as_float(n | (int)(in0 << 8) | (int)(in1 << 9)), 0.f);
+            }
+        }
+        // phase 2, whole warp: up to three needy envs per pass, lanes 0-9 / 10-19 / 20-29 = the ten rays of slot 0 / 1 / 2
+        unsigned need = __ballot_sync(kFull, needy && !big);
+        __syncwarp();
+        while (need) {
+            const int s0 = __ffs(need) - 1;
+            const unsigned n1 = need & (need - 1u);
+            const int s1 = __ffs(n1) - 1;                                 // -1 when there is no second env
+            const unsigned n2 = n1 & (n1 - 1u);
+            const int s2 = __ffs(n2) - 1;
+            need = n2 & (n2 - 1u);
+            const int src = rslot == 0 ? s0 : (rslot == 1 ? s1 : (rslot == 2 ? s2 : -1));
+            if (src >= 0) {
+                const int env = src / G;
+                const float4 *row = scr + env * SCR4;
+                const float4 hdr = row[0];
+                const float ray_c = s_ray[lane], ray_s = s_ray[32 + lane];
+                const float dirx = hdr.x * ray_c - hdr.y * ray_s, diry = hdr.y * ray_c + hdr.x * ray_s;
+                const int hz = __float_as_int(hdr.z);
+                const int n = hz & 0xff;
+                bool hb0 = false, hb1 = false;
+                float v0 = L, v1 = L;
+                for (int i = 0; i < n; ++i) {       // cpPolyShapeSegmentQuery: later accepted edges overwrite earlier ones
+                    const float4 e0 = row[1 + 2 * i], e1 = row[2 + 2 * i];
+                    PlaneEval pe;
+                    pe.d = e0.x; pe.ta = e0.y; pe.nxl = e0.z; pe.nyl = e0.w; pe.len = e1.x;
+                    float val;
+                    const bool ok = ray_vs_plane(pe, dirx, diry, L, val);
+                    if (e1.y == 0.f) { if (ok) { v0 = val; hb0 = true; } }
+                    else { if (ok) { v1 = val; hb1 = true; } }
+                }
+                const bool in0 = (hz >> 8) & 1, in1 = (hz >> 9) & 1;
+                const bool hit0 = hb0 || in0, hit1 = hb1 || in1;
+                // LiDAR.query: the first bank (list order) that reports a hit wins; misses keep the old reading
+                // (sticky vals, models.py:71)
+                if (hit0 || hit1) tile_f[env * (ROW4 * 4) + CF + 6 + (lane - rslot * kBeams)] = hit0 ? (in0 ? L : v0) : (in1 ? L : v1);
             }
         }
 
@@ -200,9 +311,38 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
         const bool ov1 = valid && !(r.x + hminx > sc.bb1.z || r.x + hmaxx < sc.bb1.x || r.y + hminy > sc.bb1.w || r.y + hmaxy < sc.bb1.y);
         bool colliding = false;
         {
-            // cooperative separating-axis test, nslots envs per pass, lanes <-> bank edges.  Contact <=> no separating
-            // axis among the edge normals of both convex polygons (touching counts: GJK distance <= 0).
-            unsigned needs = __ballot_sync(kFull, gl == 0 && (ov0 || ov1));
+            // Separating-axis test.  Contact <=> no separating axis among the edge normals of both convex polygons
+            // (touching counts: GJK distance <= 0).  Per lane first: the bank edge that separated last time (or one of
+            // its neighbours) almost always still does.  Only envs for which it does not go to the cooperative pass.
+            bool ask0 = false, ask1 = false;
+            if (ov0 || ov1) {
+                float rx[kShipVerts], ry[kShipVerts];
+#pragma unroll
+                for (int j = 0; j < kShipVerts; ++j) {
+                    rx[j] = p.ship_lx[j] * c - p.ship_ly[j] * s;
+                    ry[j] = p.ship_lx[j] * s + p.ship_ly[j] * c;
+                }
+                const float4 *bE = p.bank + (size_t)r.scen * p.scen_stride4 + kBankHeader4;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    if (b ? ov1 : ov0) {
+                        const int nb = b ? sc.n1 : sc.n0;
+                        int ax = b ? axis1 : axis0;
+                        if (ax >= nb) ax = 0;
+                        bool sep = false;
+#pragma unroll 1
+                        for (int tr = 0; tr < 3 && !sep; ++tr) {                // same edge, next edge, previous edge
+                            int i = tr == 0 ? ax : (tr == 1 ? ax + 1 : ax - 1);
+                            i = i >= nb ? 0 : (i < 0 ? nb - 1 : i);
+                            sep = bank_axis_separates(__ldg(bE + b * p.maxv + i), rx, ry, r.x, r.y);
+                            if (sep) ax = i;
+                        }
+                        if (b) { axis1 = ax; ask1 = !sep; } else { axis0 = ax; ask0 = !sep; }
+                    }
+                }
+            }
+            // cooperative pass, nslots envs at a time, lanes <-> bank edges
+            unsigned needs = __ballot_sync(kFull, gl == 0 && (ask0 || ask1));
             while (needs) {
                 int src = -1, myslot = -1;
 #pragma unroll
@@ -219,7 +359,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                 const float bx = __shfl_sync(kFull, r.x, srcl), by = __shfl_sync(kFull, r.y, srcl);
                 const float bc = __shfl_sync(kFull, c, srcl), bs = __shfl_sync(kFull, s, srcl);
                 const int bscen = __shfl_sync(kFull, r.scen, srcl);
-                const int bflags = __shfl_sync(kFull, sc.n0 | (sc.n1 << 8) | ((int)ov0 << 16) | ((int)ov1 << 17), srcl);
+                const int bflags = __shfl_sync(kFull, sc.n0 | (sc.n1 << 8) | ((int)ask0 << 16) | ((int)ask1 << 17), srcl);
                 const float4 *bE = p.bank + (size_t)bscen * p.scen_stride4 + kBankHeader4;
                 float rx[kShipVerts], ry[kShipVerts];
 #pragma unroll
@@ -228,6 +368,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                     ry[j] = p.ship_lx[j] * bs + p.ship_ly[j] * bc;
                 }
                 bool coll = false;
+                unsigned sepbits[2] = {0u, 0u};
 #pragma unroll
                 for (int b = 0; b < 2; ++b) {
                     const bool do_b = act_env && ((bflags >> (16 + b)) & 1) && !coll;
@@ -235,12 +376,8 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                     const bool actl = do_b && sel < nb;
                     float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (actl) ed = __ldg(bE + b * p.maxv + sel);
-                    float m = ed.x * rx[0] + ed.y * ry[0];
-#pragma unroll
-                    for (int j = 1; j < kShipVerts; ++j) m = fminf(m, ed.x * rx[j] + ed.y * ry[j]);
-                    const float base = ed.x * (bx - ed.z) + ed.y * (by - ed.w);
-                    const unsigned sb = __ballot_sync(kFull, actl && base + m > 0.f);      // a bank edge normal separates
-                    bool sep = (sb & slotmask) != 0u;
+                    sepbits[b] = __ballot_sync(kFull, actl && bank_axis_separates(ed, rx, ry, bx, by));   // a bank edge normal separates
+                    bool sep = (sepbits[b] & slotmask) != 0u;
                     if (__ballot_sync(kFull, do_b && !sep)) {                               // rare: try the ship's edge normals
 #pragma unroll
                         for (int j = 0; j < kShipVerts; ++j) {
@@ -254,7 +391,14 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                     if (do_b && !sep) coll = true;
                 }
                 const unsigned res = __ballot_sync(kFull, coll);
-                if (myslot >= 0 && ((res >> (myslot * lps)) & 1u)) colliding = true;
+                if (myslot >= 0) {
+                    const int sh = myslot * lps;
+                    if ((res >> sh) & 1u) colliding = true;
+                    const unsigned sb0 = (sepbits[0] >> sh) & (lps == 32 ? kFull : ((1u << lps) - 1u));
+                    const unsigned sb1 = (sepbits[1] >> sh) & (lps == 32 ? kFull : ((1u << lps) - 1u));
+                    if (sb0) axis0 = __ffs(sb0) - 1;                                        // remember the separating edges
+                    if (sb1) axis1 = __ffs(sb1) - 1;
+                }
             }
         }
         bool goal_reached = false;
@@ -318,6 +462,7 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
                 hminx = p.ship_aabb[0]; hminy = p.ship_aabb[1]; hmaxx = p.ship_aabb[2]; hmaxy = p.ship_aabb[3];
                 hx = 0.5f * (hmaxx - hminx); hy = 0.5f * (hmaxy - hminy);
                 cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
+                axis0 = 0; axis1 = 0;
                 closest_goal(r, gx, gy);
                 goals_dirty = true;
             }
@@ -341,18 +486,25 @@ __global__ void __launch_bounds__(kThreads) step_kernel(const __grid_constant__ 
         }
         __syncwarp();
         if (p.obs) {
-            float4 *o = p.obs + ((size_t)k * p.N + warp_env0) * OBS4;
-            const int n_rows = min(EPW, p.N - warp_env0);
+            float4 *o = p.obs + ((size_t)k * p.N + warp_env0) * OBS4 + lane;
+            if (EPW * OBS4 >= 32) {
+                // lane -> (row lane / OBS4, column lane % OBS4); each further round moves 32 / OBS4 rows down
 #pragma unroll
-            for (int f = lane; f < EPW * OBS4; f += 32) {
-                const int rr = f / OBS4, cc = f - rr * OBS4;
-                if (rr < n_rows) __stcs(o + f, tile[rr * ROW4 + cc]);
+                for (int i = 0; i < EPW * OBS4 / 32; ++i)
+                    if (cp_row0 + i * (32 / OBS4) < n_rows) __stcs(o + i * 32, tile[cp_src0 + i * (32 / OBS4) * ROW4]);
+            } else if (lane < EPW * OBS4 && cp_row0 < n_rows) {
+                __stcs(o, tile[cp_src0]);
             }
         }
         if (leader) {
             const size_t row = (size_t)k * p.N + e;
             if (p.reward) p.reward[row] = reward;
             if (p.done) p.done[row] = done ? 1 : 0;
+        }
+        {   // the next step's ray pass will want the double planes of these edges: pull them towards L1 now
+            const EdgeD *E = p.edges_d + (size_t)r.scen * (2 * kMaxHull);
+            if (cell.x) prefetch_l1(E + (__ffs(cell.x) - 1));
+            if (cell.y) prefetch_l1(E + kMaxHull + (__ffs(cell.y) - 1));
         }
         __syncwarp();                                           // copy-out done before the next step rewrites the tile
     }
