@@ -20,6 +20,7 @@ struct shipsim_handle {
     float4 *d_bank = nullptr;
     EdgeD *d_edges = nullptr;
     uint4 *d_grid = nullptr;
+    float4 *d_spawn = nullptr;
     int lanes = 1;
     // staging for shipsim_step_host (allocated on first use, sized for the largest K seen)
     int32_t *d_act = nullptr; float *d_obs = nullptr; float *d_rew = nullptr; uint8_t *d_done = nullptr;
@@ -208,7 +209,7 @@ extern "C" int shipsim_destroy(shipsim_t *h)
 {
     if (!h) return SHIPSIM_OK;
     DeviceGuard g(h->device);
-    cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
+    cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_spawn); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
     delete h;
     return SHIPSIM_OK;
 }
@@ -269,13 +270,15 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
     float4 *d = nullptr;
     EdgeD *de = nullptr;
     uint4 *dg = nullptr;
+    float4 *dsp = nullptr;
     double *dxy = nullptr;
     int *dn = nullptr;
     const size_t grid_cells = (size_t)n_scen * kGridN * kGridN;
-    auto cleanup = [&]() { cudaFree(d); cudaFree(de); cudaFree(dg); cudaFree(dxy); cudaFree(dn); };
+    auto cleanup = [&]() { cudaFree(d); cudaFree(de); cudaFree(dg); cudaFree(dsp); cudaFree(dxy); cudaFree(dn); };
     cudaError_t e = cudaMalloc(&d, host.size() * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&de, edges.size() * sizeof(EdgeD));
     if (e == cudaSuccess) e = cudaMalloc(&dg, grid_cells * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMalloc(&dsp, (size_t)n_scen * (1 + 2 * 4) * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&dxy, rxy.size() * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&dn, (size_t)n_scen * 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(d, host.data(), host.size() * sizeof(float4), cudaMemcpyHostToDevice);
@@ -290,14 +293,20 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
         const double reach = std::max((double)h->cfg.lidar_distance, std::sqrt(cw * cw + ch * ch)) + margin;
         e = launch_build_grid(dxy, dn, n_scen, dev_maxv, (double)h->p.gridp.x0, (double)h->p.gridp.y0, cw, ch, reach, margin, dg, 0);
     }
+    if (e == cudaSuccess) {
+        // plane phase at the spawn pose of every scenario (what an env that is reset inside the kernel starts from)
+        StepParams q = h->p;
+        q.bank = d; q.edges_d = de; q.grid = dg; q.n_scen = n_scen; q.maxv = dev_maxv; q.scen_stride4 = stride4;
+        e = launch_build_spawn_rows(q, dsp, 0);
+    }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();           // also: no launch may still be reading the old bank
     if (e != cudaSuccess) { cleanup(); return fail(SHIPSIM_ERR_CUDA, cudaGetErrorString(e)); }
     cudaFree(dxy); cudaFree(dn);
-    cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid);
-    h->d_bank = d; h->d_edges = de; h->d_grid = dg;
-    h->p.bank = d; h->p.edges_d = de; h->p.grid = dg;
+    cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_spawn);
+    h->d_bank = d; h->d_edges = de; h->d_grid = dg; h->d_spawn = dsp;
+    h->p.bank = d; h->p.edges_d = de; h->p.grid = dg; h->p.spawn_rows = dsp;
     h->p.n_scen = n_scen; h->p.maxv = dev_maxv; h->p.scen_stride4 = stride4;
-    h->launches++;
+    h->launches += 2;
     return SHIPSIM_OK;
 }
 

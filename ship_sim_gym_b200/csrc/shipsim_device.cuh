@@ -62,6 +62,7 @@ struct StepParams {
     const float4 *bank;          // packed scenario records
     const EdgeD *edges_d;        // [n_scen][2][kMaxHull] double planes
     const uint4 *grid;           // [n_scen][kGridN*kGridN] reach grid
+    const float4 *spawn_rows;    // [n_scen][1 + 2*kMaxCand] plane-phase output at the spawn pose
     GridParams gridp;
     const void *actions;         // [K][N]
     float4 *obs;                 // [K][N][4*history]
@@ -90,7 +91,6 @@ struct StepParams {
 struct EnvRegs {
     float x, y, th, vx, vy, w, ret;
     int rudder, alive, steps, scen, episode;
-    float lid[kBeams];
     float g[2 * kGoals];
 };
 
@@ -155,33 +155,33 @@ __device__ __forceinline__ int pack_bits(int rudder, int alive, int steps)
     return ((rudder / 5 + 2) & 7) | ((alive & 31) << 3) | (steps << 8);
 }
 
-__device__ __forceinline__ void load_env(const StepParams &p, int e, EnvRegs &r)
+__device__ __forceinline__ void load_env(const StepParams &p, int e, EnvRegs &r, float4 &l0, float4 &l1, float4 &l2)
 {
     const float4 *s = p.state;
     const size_t N = (size_t)p.N;
-    const float4 a = s[0 * N + e], b = s[1 * N + e], l0 = s[2 * N + e], l1 = s[3 * N + e], l2 = s[4 * N + e];
+    const float4 a = s[0 * N + e], b = s[1 * N + e];
+    l0 = s[2 * N + e]; l1 = s[3 * N + e]; l2 = s[4 * N + e];       // lidar[0..9], bits(scenario), bits(episode)
     const float4 g0 = s[5 * N + e], g1 = s[6 * N + e], g2 = s[7 * N + e];
     r.x = a.x; r.y = a.y; r.th = a.z; r.vx = a.w;
     r.vy = b.x; r.w = b.y; r.ret = b.z;
     const int bits = __float_as_int(b.w);
     r.rudder = ((bits & 7) - 2) * 5; r.alive = (bits >> 3) & 31; r.steps = bits >> 8;
-    r.lid[0] = l0.x; r.lid[1] = l0.y; r.lid[2] = l0.z; r.lid[3] = l0.w;
-    r.lid[4] = l1.x; r.lid[5] = l1.y; r.lid[6] = l1.z; r.lid[7] = l1.w;
-    r.lid[8] = l2.x; r.lid[9] = l2.y; r.scen = __float_as_int(l2.z); r.episode = __float_as_int(l2.w);
+    r.scen = __float_as_int(l2.z); r.episode = __float_as_int(l2.w);
     r.g[0] = g0.x; r.g[1] = g0.y; r.g[2] = g0.z; r.g[3] = g0.w;
     r.g[4] = g1.x; r.g[5] = g1.y; r.g[6] = g1.z; r.g[7] = g1.w;
     r.g[8] = g2.x; r.g[9] = g2.y;
 }
 
-__device__ __forceinline__ void store_env(const StepParams &p, int e, const EnvRegs &r, bool goals_dirty)
+__device__ __forceinline__ void store_env(const StepParams &p, int e, const EnvRegs &r, float4 l0, float4 l1, float l8, float l9,
+                                          bool goals_dirty)
 {
     float4 *s = p.state;
     const size_t N = (size_t)p.N;
     s[0 * N + e] = make_float4(r.x, r.y, r.th, r.vx);
     s[1 * N + e] = make_float4(r.vy, r.w, r.ret, __int_as_float(pack_bits(r.rudder, r.alive, r.steps)));
-    s[2 * N + e] = make_float4(r.lid[0], r.lid[1], r.lid[2], r.lid[3]);
-    s[3 * N + e] = make_float4(r.lid[4], r.lid[5], r.lid[6], r.lid[7]);
-    s[4 * N + e] = make_float4(r.lid[8], r.lid[9], __int_as_float(r.scen), __int_as_float(r.episode));
+    s[2 * N + e] = l0;
+    s[3 * N + e] = l1;
+    s[4 * N + e] = make_float4(l8, l9, __int_as_float(r.scen), __int_as_float(r.episode));
     if (goals_dirty) {           // goals only change on reset
         s[5 * N + e] = make_float4(r.g[0], r.g[1], r.g[2], r.g[3]);
         s[6 * N + e] = make_float4(r.g[4], r.g[5], r.g[6], r.g[7]);
@@ -199,8 +199,6 @@ __device__ __forceinline__ void reset_env(const StepParams &p, EnvRegs &r, int s
     r.g[8] = g2.x; r.g[9] = g2.y;
     r.x = p.spawn_x; r.y = p.spawn_y; r.th = 0.f; r.vx = 0.f; r.vy = 0.f; r.w = 0.f; r.ret = 0.f;
     r.rudder = 0; r.alive = (1 << kGoals) - 1; r.steps = 0; r.scen = scen; r.episode = episode;
-#pragma unroll
-    for (int i = 0; i < kBeams; ++i) r.lid[i] = -1.f;         // models.py:36
 }
 
 // ShipGame.closest_goal (game.py:333-349): first strict minimum wins; (-1,-1) when none (ship_env.py:103-107)

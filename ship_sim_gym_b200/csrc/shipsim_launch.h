@@ -15,6 +15,7 @@ cudaError_t launch_reset(const StepParams &p, const uint8_t *mask, const int *sc
                          cudaStream_t stream);
 cudaError_t launch_build_grid(const double *hull_xy, const int *hull_n, int n_scen, int maxv_in, double gx0, double gy0,
                               double cw, double ch, double reach, double touch_margin, uint4 *grid, cudaStream_t stream);
+cudaError_t launch_build_spawn_rows(const StepParams &p, float4 *rows, cudaStream_t stream);
 cudaError_t launch_stats_reduce(double *slots, double *out, int clear, cudaStream_t stream);
 
 }  // namespace shipsim
