@@ -370,6 +370,29 @@ def extra_configs(torch, dev, rank, world):
     res["sharded_1048576_K1"] = {"env_steps_per_s": rate1, "launch_ms": ms1, "K": 1,
                                  "roofline_frac_per_gpu": rate1 / world * b_alg(1) / 1e9 / peak}
     env.close()
+    # configs[4]: MLP policy + 16,384 envs on the same GPU, 128-step rollouts replayed from ONE CUDA graph: no host
+    # round-trip per step (rank 0 only; nothing here is the headline)
+    if rank == 0:
+        from ship_sim_gym_b200.rollout import MlpPolicy, RolloutCollector
+        n, T = 16384, 128
+        env = BatchedShipEnv(n, bank=bank, seed=SEED, device=dev, validate_actions=False)
+        torch.manual_seed(SEED)
+        col = RolloutCollector(env, MlpPolicy().to(dev), T=T, use_graph=True)
+        col.collect()
+        col.collect()
+        torch.cuda.synchronize()
+        reps = 5
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            col.collect()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        res["policy_rollout_16384"] = {"env_steps_per_s": n * T / (ms * 1e-3), "rollout_ms": ms, "T": T,
+                                       "policy": "MlpPolicy 32-64-64 tanh (pi, vf), Gumbel-max sampling, GAE on device",
+                                       "host_syncs_per_rollout": 0, "cuda_graph": True}
+        env.close()
     return res
 
 

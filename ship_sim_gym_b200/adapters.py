@@ -1,0 +1,106 @@
+"""Vector-env adapters for the reference's callers.
+
+`ShipVecEnv` duck-types the stable-baselines 2.x `VecEnv` protocol that `SubprocVecEnv([make_env() ...])` provides
+in train/stable_baselines/ppo.py:122-123 (`num_envs`, `observation_space`, `action_space`, `reset()`,
+`step_async(actions)`, `step_wait() -> (obs [N,32], rews [N], dones [N], infos)`, `close()`), including its worker
+semantics: the observation returned on a done step is already the reset observation.
+
+`ShipVectorEnv` duck-types the RLlib 0.6 `VectorEnv` protocol (`vector_reset()`, `reset_at(i)`,
+`vector_step(actions)`, `get_unwrapped()`) used by `tune.register_env(..., env_creator)` in train/rllib/ppo.py:21-24.
+
+Neither library is a dependency (neither is installable here); the classes only implement the methods those
+libraries call.  Both sit on one `BatchedShipEnv`, i.e. one GPU; numpy in / numpy out by default, CUDA tensors when
+`as_tensors=True` (a policy that lives on the same GPU then never touches the host).
+"""
+import numpy as np
+import torch
+
+from .env import BatchedShipEnv
+
+
+class ShipVecEnv(object):
+    """stable-baselines `VecEnv` over a BatchedShipEnv (auto-reset on, like a SubprocVecEnv worker)."""
+
+    def __init__(self, num_envs, game_config=None, env_config=None, as_tensors=False, **kw):
+        kw["auto_reset"] = True
+        self.batch = BatchedShipEnv(num_envs, game_config, env_config, **kw)
+        self.num_envs = self.batch.num_envs
+        self.observation_space = self.batch.observation_space
+        self.action_space = self.batch.action_space
+        self.as_tensors = bool(as_tensors)
+        self._pending = None
+        self._infos = [{} for _ in range(self.num_envs)]       # ShipEnv.step's info is always {} (ship_env.py:156)
+
+    def _out(self, t):
+        return t if self.as_tensors else t.cpu().numpy()
+
+    def reset(self):
+        return self._out(self.batch.reset())
+
+    def step_async(self, actions):
+        if self._pending is not None:
+            raise RuntimeError("step_async called twice without step_wait")
+        a = torch.as_tensor(np.asarray(actions) if not torch.is_tensor(actions) else actions)
+        self._pending = self.batch.step(a)       # enqueued on the GPU; nothing is waited for here
+
+    def step_wait(self):
+        if self._pending is None:
+            raise RuntimeError("step_wait called before step_async")
+        obs, rew, done, _ = self._pending
+        self._pending = None
+        return self._out(obs), self._out(rew), self._out(done), self._infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.batch.close()
+
+    # the rest of the VecEnv surface stable-baselines touches
+    def get_images(self):
+        raise NotImplementedError("rendering is out of scope for the batched env")
+
+    def render(self, mode="human"):
+        return None
+
+    def seed(self, seed=None):
+        return self.batch.seed(seed)
+
+    @property
+    def unwrapped(self):
+        return self
+
+
+class ShipVectorEnv(object):
+    """RLlib `VectorEnv` over a BatchedShipEnv.  RLlib resets sub-envs itself (`reset_at`), so auto-reset is off."""
+
+    def __init__(self, num_envs, game_config=None, env_config=None, **kw):
+        kw["auto_reset"] = False
+        self.batch = BatchedShipEnv(num_envs, game_config, env_config, **kw)
+        self.num_envs = self.batch.num_envs
+        self.observation_space = self.batch.observation_space
+        self.action_space = self.batch.action_space
+
+    def vector_reset(self):
+        obs = self.batch.reset().cpu().numpy()
+        return [obs[i] for i in range(self.num_envs)]
+
+    def reset_at(self, index):
+        mask = torch.zeros(self.num_envs, dtype=torch.uint8)
+        mask[int(index)] = 1
+        obs = self.batch.reset(mask=mask)
+        return obs[int(index)].cpu().numpy()
+
+    def vector_step(self, actions):
+        a = torch.as_tensor(np.asarray(actions, dtype=np.int64))
+        obs, rew, done, _ = self.batch.step(a)
+        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        n = self.num_envs
+        return [obs[i] for i in range(n)], [float(rew[i]) for i in range(n)], [bool(done[i]) for i in range(n)], [{} for _ in range(n)]
+
+    def get_unwrapped(self):
+        return []
+
+    def close(self):
+        self.batch.close()

@@ -222,12 +222,14 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
     const int e = warp_env0 + grp;
     const bool valid = e < p.N;
     const bool leader = valid && gl == 0;
-    float4 *tile = s_tile + warp * EPW * ROW4;
-    float4 *row4 = tile + grp * ROW4;
-    float *tile_f = reinterpret_cast<float *>(tile);
-    float4 *scr = s_scr + warp * EPW * kScr4;
-    float4 *myscr = scr + grp * kScr4;
-    float *stat = s_stat[warp];
+    // shared memory is always addressed as array + integer offset so that it stays in the shared window
+    const int tile0 = warp * EPW * ROW4;         // this warp's tile rows
+    const int row0 = tile0 + grp * ROW4;         // this env's [older frame | newest frame]
+    const int scr0 = warp * EPW * kScr4;         // this warp's scratch rows
+    const int my0 = scr0 + grp * kScr4;
+#define row4 (s_tile + row0)
+#define myscr (s_scr + my0)
+#define stat (s_stat[warp])
     const float L = p.lidar_len;
 
     // lane roles in the cooperative passes
@@ -277,6 +279,11 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
     for (int k = -1; k < p.K; ++k) {
         const bool live = k >= 0;
         float dvx = 0.f, dvy = 0.f, dw = 0.f;
+        {   // the plane phase further down will want the double planes of these edges: pull them towards L1 now
+            const EdgeD *E = p.edges_d + (size_t)r.scen * (2 * kMaxHull);
+            if (cell.x) prefetch_l1(E + (__ffs(cell.x) - 1));
+            if (cell.y) prefetch_l1(E + kMaxHull + (__ffs(cell.y) - 1));
+        }
         if (live) {
             const int a = a_next;
             ap += act_stride;
@@ -295,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
             const bool big = leader && (hz_own & kHdrBig);
             unsigned need = __ballot_sync(kFull, leader && (hz_own & 0x3ff) != 0);
             if (HIST == 2) __syncwarp();        // the frame copy has read the old readings before any lane overwrites them
-            if (big) ray_query_serial(p, myscr, tile_f + grp * (ROW4 * 4) + CF + 6);
+            if (big) ray_query_serial(p, myscr, reinterpret_cast<float *>(s_tile + row0) + CF + 6);
             while (need) {
                 const int s0 = __ffs(need) - 1;
                 const unsigned n1 = need & (need - 1u);
@@ -306,8 +313,8 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
                 const int src = rslot == 0 ? s0 : (rslot == 1 ? s1 : (rslot == 2 ? s2 : -1));
                 if (src >= 0) {
                     const int env = src / G;
-                    const float4 *row = scr + env * kScr4;
-                    const float4 hdr = row[0];
+                    const int rw = scr0 + env * kScr4;
+                    const float4 hdr = s_scr[rw];
                     const float ray_c = s_ray[lane], ray_s = s_ray[32 + lane];
                     const float dirx = hdr.x * ray_c - hdr.y * ray_s, diry = hdr.y * ray_c + hdr.x * ray_s;
                     const int hz = __float_as_int(hdr.z);
@@ -315,8 +322,8 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
                     float v0 = -1.f, v1 = -1.f;                         // hit distance per bank (< 0: none)
 #pragma unroll 1
                     for (int i = 0; i < n; ++i) {   // cpPolyShapeSegmentQuery: later accepted edges overwrite earlier ones
-                        const float4 e0 = row[1 + 2 * i];
-                        const float2 e1 = *reinterpret_cast<const float2 *>(row + 2 + 2 * i);
+                        const float4 e0 = s_scr[rw + 1 + 2 * i];
+                        const float2 e1 = *reinterpret_cast<const float2 *>(s_scr + rw + 2 + 2 * i);
                         float val;
                         const bool ok = ray_vs_plane(e0.x, e0.y, e0.z, e0.w, e1.x, dirx, diry, L, val);
                         if (ok && e1.y == 0.f) v0 = val;
@@ -327,7 +334,7 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
                     // LiDAR.query: the first bank (list order) that reports a hit wins; misses keep the old reading
                     // (sticky vals, models.py:71)
                     const float v = v0 >= 0.f ? v0 : v1;
-                    if (v >= 0.f) tile_f[env * (ROW4 * 4) + CF + 6 + rj] = v;
+                    if (v >= 0.f) reinterpret_cast<float *>(s_tile + tile0 + env * ROW4)[CF + 6 + rj] = v;
                 }
             }
             __syncwarp();                       // the rows have been read: the plane phase may overwrite them
@@ -472,6 +479,20 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
                 }
             }
 
+        }
+        // ---- cpSpaceStep of the NEXT step, positions first (cpBodyUpdatePosition).  Done before this step's outputs
+        // so that the grid cell of the new pose is requested as early as possible: it is consumed an iteration later.
+        const float fx = r.x, fy = r.y, fth = r.th;                 // this step's pose, for the observation frame
+        if (k + 1 < p.K) {
+            cpre = c; spre = s;
+            r.x += r.vx * p.dt;
+            r.y += r.vy * p.dt;
+            r.th += r.w * p.dt;
+            sincos_fast(r.th, s, c);
+            hull_half_extents(p, c, s, hx, hy);
+            cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
+        }
+        if (live) {
             // ---- outputs.  The leader completes the newest frame in the resident tile (lidar slots are already there);
             // obs rows of the warp's envs are contiguous in global memory, so the tile is copied out with fully
             // coalesced 128-bit streaming stores.
@@ -485,7 +506,7 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
                 } else {
                     reinterpret_cast<float2 *>(row4 + OBS4 - 3)[0] = make_float2(gx, gy);
                 }
-                row4[OBS4 - 4] = make_float4(r.x, r.y, (float)r.rudder, r.th);
+                row4[OBS4 - 4] = make_float4(fx, fy, (float)r.rudder, fth);
             }
             __syncwarp();
             if (p.obs) {
@@ -494,9 +515,9 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
                     // lane -> (row lane / OBS4, column lane % OBS4); each further round moves 32 / OBS4 rows down
 #pragma unroll
                     for (int i = 0; i < EPW * OBS4 / 32; ++i)
-                        if (cp_row0 + i * (32 / OBS4) < n_rows) __stcs(o + i * 32, tile[cp_src0 + i * (32 / OBS4) * ROW4]);
+                        if (cp_row0 + i * (32 / OBS4) < n_rows) __stcs(o + i * 32, s_tile[tile0 + cp_src0 + i * (32 / OBS4) * ROW4]);
                 } else if (lane < EPW * OBS4 && cp_row0 < n_rows) {
-                    __stcs(o, tile[cp_src0]);
+                    __stcs(o, s_tile[tile0 + cp_src0]);
                 }
             }
             if (leader) {
@@ -506,23 +527,14 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
             }
         }
         __syncwarp();                           // copy-out done and scratch rows complete before the next iteration
-
-        // ---- cpSpaceStep of the NEXT step, positions first (cpBodyUpdatePosition); its grid cell is requested now
-        // and consumed a whole iteration later
-        if (k + 1 < p.K) {
-            cpre = c; spre = s;
-            r.x += r.vx * p.dt;
-            r.y += r.vy * p.dt;
-            r.th += r.w * p.dt;
-            sincos_fast(r.th, s, c);
-            hull_half_extents(p, c, s, hx, hy);
-            cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
-        }
     }
+    // the loop leaves the pose of the last step in r (no integration after it)
     if (leader) {
         const float4 l1 = row4[OBS4 - 3], l2 = row4[OBS4 - 2], l3 = row4[OBS4 - 1];
         store_env(p, e, r, make_float4(l1.z, l1.w, l2.x, l2.y), make_float4(l2.z, l2.w, l3.x, l3.y), l3.z, l3.w, goals_dirty);
     }
+#undef row4
+#undef myscr
 
     // episode statistics: one red.add per non-zero value per warp into a slot row
     __syncwarp();
@@ -530,6 +542,7 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
         const float v = stat[lane];
         if (v != 0.f) atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * kStatLen + lane, (double)v);
     }
+#undef stat
 }
 
 // plane phase at the spawn pose of every scenario (what a reset env starts from), one thread per scenario

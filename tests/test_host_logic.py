@@ -1,0 +1,62 @@
+"""CPU only: the host-side mirror of the reference interface -- config knobs (ship_gym/config.py:8-24), the
+curriculum helper (ship_gym/curriculum.py:23-50) and the gym-space stand-ins (ship_env.py:19,48)."""
+import numpy as np
+import pytest
+
+from ship_sim_gym_b200 import config, curriculum
+
+
+def test_config_defaults_are_the_reference_values():
+    assert config.GameConfig.SPEED == 10 and config.GameConfig.BOUNDS == (600, 600) and config.GameConfig.FPS == 1000
+    assert config.EnvConfig.HISTORY_SIZE == 2 and config.EnvConfig.MAX_STEPS == 1000
+    assert (config.LidarConfig.N_BEAMS, config.LidarConfig.DISTANCE, config.LidarConfig.ANGULAR_SPREAD) == (10, 100, 180)
+    k = config.snapshot()
+    assert (k["W"], k["H"], k["speed"], k["history"], k["max_steps"]) == (600.0, 600.0, 10.0, 2, 1000)
+    # the reference builds LiDAR with its constructor defaults and never reads LidarConfig (models.py:29,149-150)
+    assert k["lidar"] == dict(N_BEAMS=10, DISTANCE=100, ANGULAR_SPREAD=90)
+    assert config.snapshot(honour_lidar_config=True)["lidar"]["ANGULAR_SPREAD"] == 180.0
+
+
+def test_config_classes_are_used_as_mutable_singletons_but_snapshotted():
+    class GC(config.GameConfig):
+        pass
+    GC.SPEED = 30                      # train/stable_baselines/ppo.py:65-69 idiom
+    GC.BOUNDS = (1000, 1000)
+    k = config.snapshot(GC, config.EnvConfig)
+    GC.SPEED = 1
+    assert k["speed"] == 30.0 and (k["W"], k["H"]) == (1000.0, 1000.0)
+    assert config.BASE_DT * k["speed"] == pytest.approx(3.0)          # game.py:27,194
+
+
+def test_history_size_must_be_positive():
+    class EC(config.EnvConfig):
+        HISTORY_SIZE = 0
+    with pytest.raises(ValueError):                                   # ship_env.py:46-47
+        config.snapshot(None, EC)
+
+
+def test_curriculum_semantics_incl_quirks():
+    c = curriculum.Curriculum([100, 200, 400], [0.2, 0.5], repeat_condition=1)
+    assert int(c) == 100 and float(c) == 100.0
+    assert not c.progress(0.2)                 # strict '>' (curriculum.py:44)
+    assert not c.progress(0.3)                 # first pass: counter 1, needs repeat_condition + 1 passes
+    assert not c.progress(0.1)                 # a failing call does NOT reset the counter (quirk Q27)
+    assert c.progress(0.3) and int(c) == 200   # second pass advances
+    assert not c.progress(0.9)
+    assert c.progress(0.9) and int(c) == 400
+    assert not c.progress(5.0) and int(c) == 400          # no lesson left
+    lesson = curriculum.Lesson({"reward": 0.5, "steps": 10})
+    assert lesson.pass_lesson({"reward": 0.5, "steps": 11}) and not lesson.pass_lesson({"reward": 0.4, "steps": 11})
+    assert curriculum.LessonCondition.STEPS.value == 0 and curriculum.LessonCondition.REWARD.value == 1
+
+
+def test_space_stand_ins():
+    pytest.importorskip("torch")
+    from ship_sim_gym_b200.env import Box, Discrete
+    d = Discrete(3)                                                   # ship_env.py:19
+    assert d.contains(0) and d.contains(np.int64(2)) and not d.contains(3) and not d.contains(-1)
+    assert not d.contains(1.0) and not d.contains(True)
+    d.seed(0)
+    assert all(0 <= d.sample() < 3 for _ in range(50))
+    b = Box(0, 600, (32,), np.uint8)                                  # ship_env.py:48
+    assert b.shape == (32,) and b.high.max() == 600 and b.dtype == np.uint8
