@@ -121,7 +121,6 @@ def test_policy_rollout_graph_replay_matches_eager():
     assert out[0][3] == T and out[1][3] == 0
     # same physics either way: every transition obeys the env's invariants
     for rew, done, obs, _ in out:
-        assert set(torch.unique(rew).tolist()) <= {1.0, -1.0, pytest.approx(-0.01)} or True
         r = rew.cpu().numpy()
         assert np.isin(np.round(r, 4), [1.0, -1.0, -0.01]).all()
         first = obs[1:, :, :16].cpu().numpy()
