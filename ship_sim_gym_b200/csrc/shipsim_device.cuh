@@ -91,7 +91,6 @@ struct StepParams {
 struct EnvRegs {
     float x, y, th, vx, vy, w, ret;
     int rudder, alive, steps, scen, episode;
-    float g[2 * kGoals];
 };
 
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
@@ -155,25 +154,23 @@ __device__ __forceinline__ int pack_bits(int rudder, int alive, int steps)
     return ((rudder / 5 + 2) & 7) | ((alive & 31) << 3) | (steps << 8);
 }
 
-__device__ __forceinline__ void load_env(const StepParams &p, int e, EnvRegs &r, float4 &l0, float4 &l1, float4 &l2)
+// goals travel as the three raw float4 planes (g0 = goal0.xy goal1.xy, g1 = goal2.xy goal3.xy, g2 = goal4.xy, -, -)
+__device__ __forceinline__ void load_env(const StepParams &p, int e, EnvRegs &r, float4 &l0, float4 &l1, float4 &l2, float4 &g0,
+                                         float4 &g1, float4 &g2)
 {
     const float4 *s = p.state;
     const size_t N = (size_t)p.N;
     const float4 a = s[0 * N + e], b = s[1 * N + e];
     l0 = s[2 * N + e]; l1 = s[3 * N + e]; l2 = s[4 * N + e];       // lidar[0..9], bits(scenario), bits(episode)
-    const float4 g0 = s[5 * N + e], g1 = s[6 * N + e], g2 = s[7 * N + e];
+    g0 = s[5 * N + e]; g1 = s[6 * N + e]; g2 = s[7 * N + e];
     r.x = a.x; r.y = a.y; r.th = a.z; r.vx = a.w;
     r.vy = b.x; r.w = b.y; r.ret = b.z;
     const int bits = __float_as_int(b.w);
     r.rudder = ((bits & 7) - 2) * 5; r.alive = (bits >> 3) & 31; r.steps = bits >> 8;
     r.scen = __float_as_int(l2.z); r.episode = __float_as_int(l2.w);
-    r.g[0] = g0.x; r.g[1] = g0.y; r.g[2] = g0.z; r.g[3] = g0.w;
-    r.g[4] = g1.x; r.g[5] = g1.y; r.g[6] = g1.z; r.g[7] = g1.w;
-    r.g[8] = g2.x; r.g[9] = g2.y;
 }
 
-__device__ __forceinline__ void store_env(const StepParams &p, int e, const EnvRegs &r, float4 l0, float4 l1, float l8, float l9,
-                                          bool goals_dirty)
+__device__ __forceinline__ void store_env(const StepParams &p, int e, const EnvRegs &r, float4 l0, float4 l1, float l8, float l9)
 {
     float4 *s = p.state;
     const size_t N = (size_t)p.N;
@@ -182,37 +179,41 @@ __device__ __forceinline__ void store_env(const StepParams &p, int e, const EnvR
     s[2 * N + e] = l0;
     s[3 * N + e] = l1;
     s[4 * N + e] = make_float4(l8, l9, __int_as_float(r.scen), __int_as_float(r.episode));
-    if (goals_dirty) {           // goals only change on reset
-        s[5 * N + e] = make_float4(r.g[0], r.g[1], r.g[2], r.g[3]);
-        s[6 * N + e] = make_float4(r.g[4], r.g[5], r.g[6], r.g[7]);
-        s[7 * N + e] = make_float4(r.g[8], r.g[9], 0.f, 0.f);
-    }
 }
 
-// ShipGame.reset + ShipEnv.reset for one env (game.py:260-277, ship_env.py:171-184); goals come from the bank.
+__device__ __forceinline__ void store_goals(const StepParams &p, int e, float4 g0, float4 g1, float4 g2)   // goals only change on reset
+{
+    float4 *s = p.state;
+    const size_t N = (size_t)p.N;
+    s[5 * N + e] = g0; s[6 * N + e] = g1; s[7 * N + e] = make_float4(g2.x, g2.y, 0.f, 0.f);
+}
+
+// ShipGame.reset + ShipEnv.reset for one env (game.py:260-277, ship_env.py:171-184); the goals come from the bank
+// record of `scen` (float4 2..4) and are handled by the caller.
 __device__ __forceinline__ void reset_env(const StepParams &p, EnvRegs &r, int scen, int episode)
 {
-    const float4 *sc = p.bank + (size_t)scen * p.scen_stride4;
-    const float4 g0 = __ldg(sc + 2), g1 = __ldg(sc + 3), g2 = __ldg(sc + 4);
-    r.g[0] = g0.x; r.g[1] = g0.y; r.g[2] = g0.z; r.g[3] = g0.w;
-    r.g[4] = g1.x; r.g[5] = g1.y; r.g[6] = g1.z; r.g[7] = g1.w;
-    r.g[8] = g2.x; r.g[9] = g2.y;
     r.x = p.spawn_x; r.y = p.spawn_y; r.th = 0.f; r.vx = 0.f; r.vy = 0.f; r.w = 0.f; r.ret = 0.f;
     r.rudder = 0; r.alive = (1 << kGoals) - 1; r.steps = 0; r.scen = scen; r.episode = episode;
 }
 
 // ShipGame.closest_goal (game.py:333-349): first strict minimum wins; (-1,-1) when none (ship_env.py:103-107)
-__device__ __forceinline__ void closest_goal(const EnvRegs &r, float &gx, float &gy)
+__device__ __forceinline__ void closest_goal(const float2 (&g)[kGoals], int alive, float x, float y, float &gx, float &gy)
 {
     float best = 3.0e38f;
     gx = -1.f; gy = -1.f;
 #pragma unroll
     for (int k = 0; k < kGoals; ++k) {
-        const float dx = r.g[2 * k] - r.x, dy = r.g[2 * k + 1] - r.y;
+        const float dx = g[k].x - x, dy = g[k].y - y;
         const float d2 = dx * dx + dy * dy;
-        const bool take = ((r.alive >> k) & 1) && d2 < best;
-        if (take) { best = d2; gx = r.g[2 * k]; gy = r.g[2 * k + 1]; }
+        const bool take = ((alive >> k) & 1) && d2 < best;
+        if (take) { best = d2; gx = g[k].x; gy = g[k].y; }
     }
+}
+
+__device__ __forceinline__ void unpack_goals(float4 g0, float4 g1, float4 g2, float2 (&g)[kGoals])
+{
+    g[0] = make_float2(g0.x, g0.y); g[1] = make_float2(g0.z, g0.w); g[2] = make_float2(g1.x, g1.y);
+    g[3] = make_float2(g1.z, g1.w); g[4] = make_float2(g2.x, g2.y);
 }
 
 // Circle-vs-poly contact (CircleToPoly): distance(goal centre, ship polygon) <= goal radius, evaluated in the
@@ -242,6 +243,14 @@ __device__ __forceinline__ bool goal_touches_ship(const StepParams &p, float qx,
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
+// 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, completes in the background
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // order-preserving float <-> int map for __reduce_min_sync
 __device__ __forceinline__ int f2ord(float f) { const int k = __float_as_int(f); return k ^ ((k >> 31) & 0x7fffffff); }

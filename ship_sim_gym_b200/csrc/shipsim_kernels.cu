@@ -72,10 +72,8 @@ __device__ __forceinline__ uint4 load_cell(const StepParams &p, int scen, float 
 // reference's cpSplittingPlane holds: d = n.(o - v_i), ta = cross(n, o - v_i).
 struct PlaneEval { float d, ta, nx, ny, len; };
 
-__device__ __forceinline__ PlaneEval eval_plane(const EdgeD *E, double xd, double yd, double hxd, double hyd)
+__device__ __forceinline__ PlaneEval eval_plane_rec(const double2 nd, const float4 ev, double xd, double yd, double hxd, double hyd)
 {
-    const double2 nd = __ldg(reinterpret_cast<const double2 *>(E));
-    const float4 ev = __ldg(reinterpret_cast<const float4 *>(E) + 1);
     const double qx = (xd - (double)ev.x) + hxd, qy = (yd - (double)ev.y) + hyd;     // origin - v_i
     PlaneEval o;
     o.d = (float)(nd.x * qx + nd.y * qy);
@@ -84,6 +82,11 @@ __device__ __forceinline__ PlaneEval eval_plane(const EdgeD *E, double xd, doubl
     o.ny = (float)nd.y;
     o.len = ev.z;
     return o;
+}
+
+__device__ __forceinline__ PlaneEval eval_plane(const EdgeD *E, double xd, double yd, double hxd, double hyd)
+{
+    return eval_plane_rec(__ldg(reinterpret_cast<const double2 *>(E)), __ldg(reinterpret_cast<const float4 *>(E) + 1), xd, yd, hxd, hyd);
 }
 
 __device__ __forceinline__ float rcp_approx(float x)
@@ -119,7 +122,8 @@ constexpr int kHdrIn0 = 1 << 8, kHdrIn1 = 1 << 9, kHdrBig = 1 << 10;
 //   [1+2i]   d, ta, -L*nx, -L*ny        [2+2i]  len, bank (0.f / 1.f), 0, 0
 //   big row (more than kMaxCand candidates; rays are then cast serially by the owner lane):
 //   [1]      x, y, hx, hy               [2]     bits(scen), bits(m0), bits(m1), bits(flags)
-template <bool WITH_SAT>
+// STAGED: the raw EdgeD record of candidate i has already been copied (cp.async) into row[1+2i], row[2+2i].
+template <bool WITH_SAT, bool STAGED>
 __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, float y, float hx, float hy, float c, float s, int scen,
                                                 const uint4 cell, float4 *row)
 {
@@ -148,7 +152,9 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
         int idx;
         if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
         const unsigned bbit = idx < kMaxHull ? 1u : 2u;
-        const PlaneEval pe = eval_plane(E + idx, xd, yd, hxd, hyd);
+        PlaneEval pe;
+        if (STAGED) pe = eval_plane_rec(*reinterpret_cast<const double2 *>(row + 1 + 2 * n), row[2 + 2 * n], xd, yd, hxd, hyd);
+        else pe = eval_plane(E + idx, xd, yd, hxd, hyd);
         if (pe.d > 0.f) outm |= bbit;
         if (WITH_SAT) {
             float m = pe.nx * rx[0] + pe.ny * ry[0];
@@ -203,8 +209,10 @@ __device__ __noinline__ void ray_query_serial(const StepParams &p, const float4 
     }
 }
 
-template <int G, int HIST>
-__global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(const __grid_constant__ StepParams p)
+// MINB = CTAs per SM the register allocation aims for: 5 (96 registers) pays off only when the grid is large enough
+// to fill them, otherwise 4 (128 registers, less rematerialisation).
+template <int G, int HIST, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int EPW = 32 / G;                 // envs per warp
     constexpr int OBS4 = 4 * HIST;              // float4 per obs row
@@ -213,6 +221,7 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
     constexpr int NW = kThreads / 32;
     __shared__ float4 s_tile[NW * EPW * ROW4];  // [older frame | newest frame] of every env; lidar slots = sticky vals
     __shared__ float4 s_scr[NW * EPW * kScr4];  // plane-phase output of every env
+    __shared__ float2 s_goal[NW * kGoals * EPW];    // goal centres, [warp][goal][env]: only rewritten on reset
     __shared__ float s_ray[2 * 32];
     __shared__ float s_stat[NW][8];
 
@@ -227,6 +236,7 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
     const int row0 = tile0 + grp * ROW4;         // this env's [older frame | newest frame]
     const int scr0 = warp * EPW * kScr4;         // this warp's scratch rows
     const int my0 = scr0 + grp * kScr4;
+    const int goal0 = warp * kGoals * EPW + grp;  // + g * EPW
 #define row4 (s_tile + row0)
 #define myscr (s_scr + my0)
 #define stat (s_stat[warp])
@@ -249,18 +259,21 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
 
     EnvRegs r;
     {
-        float4 l0, l1, l2;
-        load_env(p, valid ? e : p.N - 1, r, l0, l1, l2);           // lanes of idle groups shadow the last env; they never store
+        float4 l0, l1, l2, g0, g1, g2;
+        load_env(p, valid ? e : p.N - 1, r, l0, l1, l2, g0, g1, g2);   // lanes of idle groups shadow the last env; they never store
+        float2 g[kGoals];
+        unpack_goals(g0, g1, g2, g);
         float gx, gy;
-        closest_goal(r, gx, gy);
-        if (gl == 0) {                                              // newest frame of the resident tile = frame of the current state
+        closest_goal(g, r.alive, r.x, r.y, gx, gy);
+        if (gl == 0) {
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i) s_goal[goal0 + i * EPW] = g[i];                                              // newest frame of the resident tile = frame of the current state
             row4[OBS4 - 4] = make_float4(r.x, r.y, (float)r.rudder, r.th);
             row4[OBS4 - 3] = make_float4(gx, gy, l0.x, l0.y);
             row4[OBS4 - 2] = make_float4(l0.z, l0.w, l1.x, l1.y);
             row4[OBS4 - 1] = make_float4(l1.z, l1.w, l2.x, l2.y);
         }
     }
-    const long long gid = p.env_id_offset + e;
     float c, s, hx, hy;
     sincos_fast(r.th, s, c);
     hull_half_extents(p, c, s, hx, hy);
@@ -270,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
     const size_t act_esize = p.action_dtype == 1 ? 8 : (p.action_dtype == 2 ? 1 : 4);
     const size_t act_stride = (size_t)p.N * act_esize;
     const char *ap = reinterpret_cast<const char *>(p.actions) + (size_t)(valid ? e : p.N - 1) * act_esize;
-    int a_next = load_action(p, ap, 0, gid);
+    int a_next = load_action(p, ap, 0, p.env_id_offset + e);
     __syncthreads();                             // s_ray / stat visible; also orders the tile initialisation
 
     // Iteration k >= 0 is env-step k and starts with the pose ALREADY integrated (cpBodyUpdatePosition of step k);
@@ -279,15 +292,10 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
     for (int k = -1; k < p.K; ++k) {
         const bool live = k >= 0;
         float dvx = 0.f, dvy = 0.f, dw = 0.f;
-        {   // the plane phase further down will want the double planes of these edges: pull them towards L1 now
-            const EdgeD *E = p.edges_d + (size_t)r.scen * (2 * kMaxHull);
-            if (cell.x) prefetch_l1(E + (__ffs(cell.x) - 1));
-            if (cell.y) prefetch_l1(E + kMaxHull + (__ffs(cell.y) - 1));
-        }
         if (live) {
             const int a = a_next;
             ap += act_stride;
-            if (k + 1 < p.K) a_next = load_action(p, ap, k + 1, gid);                 // prefetch: off the critical path
+            if (k + 1 < p.K) a_next = load_action(p, ap, k + 1, p.env_id_offset + e);                 // prefetch: off the critical path
             // previous frame <- newest frame of the last step / reset (SURVEY.md App. A note N2); lidar stays in place
             if (HIST == 2 && gl == 0) { row4[0] = row4[4]; row4[1] = row4[5]; row4[2] = row4[6]; row4[3] = row4[7]; }
 
@@ -340,17 +348,67 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
             __syncwarp();                       // the rows have been read: the plane phase may overwrite them
         }
 
+        // ---- the candidate planes of the integrated pose: their raw records are copied global -> shared without
+        // passing through registers (cp.async) while the goal tests below run
+        const bool near_any = leader && (cell.x | cell.y | cell.z | cell.w) != 0u;
+        // (only worth it when many warps share an SM: with G > 1 the batch is small and the copy would sit on the critical path)
+        const bool staged = G == 1 && near_any && (__popc(cell.x) + __popc(cell.y) <= kMaxCand);
+        if (staged) {
+            const EdgeD *E = p.edges_d + (size_t)r.scen * (2 * kMaxHull);
+            unsigned m0 = cell.x, m1 = cell.y;
+            int n = 0;
+            while (m0 | m1) {
+                int idx;
+                if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
+                cp_async16(myscr + 1 + 2 * n, E + idx);
+                cp_async16(myscr + 2 + 2 * n, reinterpret_cast<const float4 *>(E + idx) + 1);
+                ++n;
+            }
+        }
+
+        bool done = false, do_reset = false, goal_reached = false;
+        float reward = 0.f, gx = -1.f, gy = -1.f;
+        if (live) {
+            // ---- goals (collide_goal, game.py:243-257) and the nearest remaining goal (closest_goal, game.py:333-349).
+            // The squared distance to the body origin serves both the nearest-goal search and a bounding-circle cull;
+            // only goals inside the circle are rotated into the body frame for the exact circle-vs-hull test.
+            float2 g[kGoals];
+            float gd2[kGoals];
+            unsigned cand = 0u;
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i) {
+                g[i] = s_goal[goal0 + i * EPW];
+                const float ux = g[i].x - r.x, uy = g[i].y - r.y;
+                gd2[i] = ux * ux + uy * uy;
+                if (valid && ((r.alive >> i) & 1) && gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
+            }
+            while (cand) {
+                const int i = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                float ux = g[0].x, uy = g[0].y;
+#pragma unroll
+                for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
+                ux -= r.x; uy -= r.y;
+                const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
+                if (!goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << i); }
+            }
+            float best = 3.0e38f;
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i)
+                if (((r.alive >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
+        }
+
         // ---- plane phase at the integrated pose: next step's lidar planes + this step's ship-vs-bank pre-test
+        if (G == 1) cp_async_wait_all();
         unsigned ask = 0u;
         if (leader) {
-            if ((cell.x | cell.y | cell.z | cell.w) != 0u) ask = plane_phase<true>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, myscr);
+            if (staged) ask = plane_phase<true, true>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, myscr);
+            else if (near_any) ask = plane_phase<true, false>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, myscr);
             else myscr[0] = make_float4(c, s, 0.f, 0.f);
         }
 
-        bool done = false, do_reset = false;
-        float reward = 0.f, gx = -1.f, gy = -1.f;
         if (live) {
-            // ---- overlap tests at the new pose -> begin callbacks collide_ship / collide_goal (game.py:232-257)
+            // ---- overlap test at the new pose -> begin callback collide_ship (game.py:232-241)
             bool colliding = false;
             {
                 // Separating-axis test for the envs the plane phase could not settle.  Contact <=> no separating axis
@@ -407,29 +465,6 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
                     if (myslot >= 0 && ((res >> (myslot * lps)) & 1u)) colliding = true;
                 }
             }
-            bool goal_reached = false;
-            float gd2[kGoals];
-            {
-                // goals: squared distance to the body origin serves both the closest-goal search and a bounding-circle
-                // cull; only goals inside the circle are rotated into the body frame for the exact distance test
-                unsigned cand = 0u;
-#pragma unroll
-                for (int g = 0; g < kGoals; ++g) {
-                    const float ux = r.g[2 * g] - r.x, uy = r.g[2 * g + 1] - r.y;
-                    gd2[g] = ux * ux + uy * uy;
-                    if (valid && ((r.alive >> g) & 1) && gd2[g] <= p.goal_cull_r2) cand |= 1u << g;
-                }
-                while (cand) {
-                    const int g = __ffs(cand) - 1;
-                    cand &= cand - 1u;
-                    float ux = r.g[0], uy = r.g[1];
-#pragma unroll
-                    for (int j = 1; j < kGoals; ++j) if (g == j) { ux = r.g[2 * j]; uy = r.g[2 * j + 1]; }
-                    ux -= r.x; uy -= r.y;
-                    const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
-                    if (!goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << g); }
-                }
-            }
 
             // ---- cpBodyUpdateVelocity: v = v*damping + f/m*dt, w = w*damping + t/I*dt
             r.vx = r.vx * p.damping + dvx;
@@ -441,12 +476,6 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
             reward = goal_reached ? 1.f : (oob ? -1.f : p.step_penalty);
             r.ret += reward;
             r.steps += 1;
-            {   // ShipGame.closest_goal (game.py:333-349) over the goals still alive
-                float best = 3.0e38f;
-#pragma unroll
-                for (int g = 0; g < kGoals; ++g)
-                    if (((r.alive >> g) & 1) && gd2[g] < best) { best = gd2[g]; gx = r.g[2 * g]; gy = r.g[2 * g + 1]; }
-            }
             const bool all_goals = (r.alive == 0);
             const bool timeout = (r.steps >= p.max_steps);
             done = colliding || all_goals || oob || timeout;             // ship_env.py:115-134
@@ -463,10 +492,19 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
                 }
                 if (do_reset) {
                     const int ep = r.episode + 1;
-                    reset_env(p, r, pick_scenario(p, gid, ep), ep);
+                    reset_env(p, r, pick_scenario(p, p.env_id_offset + e, ep), ep);
                     c = 1.f; s = 0.f;
                     hx = 0.5f * (p.ship_aabb[2] - p.ship_aabb[0]); hy = 0.5f * (p.ship_aabb[3] - p.ship_aabb[1]);
-                    closest_goal(r, gx, gy);
+                    {
+                        const float4 *rec = p.bank + (size_t)r.scen * p.scen_stride4;
+                        float2 g[kGoals];
+                        unpack_goals(__ldg(rec + 2), __ldg(rec + 3), __ldg(rec + 4), g);
+                        closest_goal(g, r.alive, r.x, r.y, gx, gy);
+                        if (gl == 0) {
+#pragma unroll
+                            for (int i = 0; i < kGoals; ++i) s_goal[goal0 + i * EPW] = g[i];
+                        }
+                    }
                     goals_dirty = true;
                     if (gl == 0) {              // the spawn pose's planes were evaluated when the scenario was loaded
                         const float4 *sp = p.spawn_rows + (size_t)r.scen * kScr4;
@@ -531,7 +569,12 @@ __global__ void __launch_bounds__(kThreads, SHIPSIM_MIN_BLOCKS) step_kernel(cons
     // the loop leaves the pose of the last step in r (no integration after it)
     if (leader) {
         const float4 l1 = row4[OBS4 - 3], l2 = row4[OBS4 - 2], l3 = row4[OBS4 - 1];
-        store_env(p, e, r, make_float4(l1.z, l1.w, l2.x, l2.y), make_float4(l2.z, l2.w, l3.x, l3.y), l3.z, l3.w, goals_dirty);
+        store_env(p, e, r, make_float4(l1.z, l1.w, l2.x, l2.y), make_float4(l2.z, l2.w, l3.x, l3.y), l3.z, l3.w);
+        if (goals_dirty) {
+            const float2 a0 = s_goal[goal0], a1 = s_goal[goal0 + EPW], a2 = s_goal[goal0 + 2 * EPW], a3 = s_goal[goal0 + 3 * EPW],
+                         a4 = s_goal[goal0 + 4 * EPW];
+            store_goals(p, e, make_float4(a0.x, a0.y, a1.x, a1.y), make_float4(a2.x, a2.y, a3.x, a3.y), make_float4(a4.x, a4.y, 0.f, 0.f));
+        }
     }
 #undef row4
 #undef myscr
@@ -554,7 +597,7 @@ __global__ void __launch_bounds__(128) build_spawn_rows_kernel(const __grid_cons
     for (int i = 0; i < kScr4; ++i) row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float hx = 0.5f * (p.ship_aabb[2] - p.ship_aabb[0]), hy = 0.5f * (p.ship_aabb[3] - p.ship_aabb[1]);
     const uint4 cell = load_cell(p, sidx, p.spawn_x + hx, p.spawn_y + hy);
-    if ((cell.x | cell.y | cell.z | cell.w) != 0u) plane_phase<false>(p, p.spawn_x, p.spawn_y, hx, hy, 1.f, 0.f, sidx, cell, row);
+    if ((cell.x | cell.y | cell.z | cell.w) != 0u) plane_phase<false, false>(p, p.spawn_x, p.spawn_y, hx, hy, 1.f, 0.f, sidx, cell, row);
     else row[0] = make_float4(1.f, 0.f, 0.f, 0.f);
 }
 
@@ -650,16 +693,21 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
     if (e >= p.N) return;
     if (mask && !mask[e]) return;
     EnvRegs r;
-    float4 l0, l1, l2;
-    load_env(p, e, r, l0, l1, l2);
+    float4 l0, l1, l2, g0, g1, g2;
+    load_env(p, e, r, l0, l1, l2, g0, g1, g2);
     const int ep = first ? 0 : r.episode + 1;
     const int scen = scenario ? scenario[e] : pick_scenario(p, p.env_id_offset + e, ep);
     reset_env(p, r, scen, ep);
+    const float4 *rec = p.bank + (size_t)scen * p.scen_stride4;
+    g0 = __ldg(rec + 2); g1 = __ldg(rec + 3); g2 = __ldg(rec + 4);
     const float4 neg4 = make_float4(-1.f, -1.f, -1.f, -1.f);      // models.py:36: LiDAR.vals start at -1
-    store_env(p, e, r, neg4, neg4, -1.f, -1.f, true);
+    store_env(p, e, r, neg4, neg4, -1.f, -1.f);
+    store_goals(p, e, g0, g1, g2);
     if (obs) {
         float gx, gy;
-        closest_goal(r, gx, gy);
+        float2 g[kGoals];
+        unpack_goals(g0, g1, g2, g);
+        closest_goal(g, r.alive, r.x, r.y, gx, gy);
         float4 *o = obs + (size_t)e * (4 * p.history);
         const float4 neg = make_float4(-1.f, -1.f, -1.f, -1.f);
         if (p.history == 2) { o[0] = neg; o[1] = neg; o[2] = neg; o[3] = neg; o += 4; }
@@ -693,8 +741,13 @@ static cudaError_t launch_g(const StepParams &p, cudaStream_t stream, LaunchShap
     const int envs_per_cta = kThreads / G;
     const int blocks = (p.N + envs_per_cta - 1) / envs_per_cta;
     if (shape) { shape->lanes_per_env = G; shape->threads = kThreads; shape->blocks = blocks; }
-    if (p.history == 2) step_kernel<G, 2><<<blocks, kThreads, 0, stream>>>(p);
-    else step_kernel<G, 1><<<blocks, kThreads, 0, stream>>>(p);
+    if (G == 1 && blocks >= 148 * 8) {
+        if (p.history == 2) step_kernel<G, 2, 5><<<blocks, kThreads, 0, stream>>>(p);
+        else step_kernel<G, 1, 5><<<blocks, kThreads, 0, stream>>>(p);
+    } else {
+        if (p.history == 2) step_kernel<G, 2, SHIPSIM_MIN_BLOCKS><<<blocks, kThreads, 0, stream>>>(p);
+        else step_kernel<G, 1, SHIPSIM_MIN_BLOCKS><<<blocks, kThreads, 0, stream>>>(p);
+    }
     return cudaGetLastError();
 }
 
