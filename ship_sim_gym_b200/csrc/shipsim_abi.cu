@@ -259,6 +259,7 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
                 if (!(ln > 0)) return fail(SHIPSIM_ERR_ARG, "degenerate hull edge");
                 E[i] = make_float4((float)(ey / ln), (float)(-ex / ln), (float)bx, (float)by);   // cpvrperp: outward for CCW
                 ED[i].nx = ey / ln; ED[i].ny = -ex / ln; ED[i].vx = (float)bx; ED[i].vy = (float)by; ED[i].len = (float)ln;
+                { const int self = b * kMaxHull + i; std::memcpy(&ED[i].pad, &self, 4); }
             }
         }
         const double *g = goals_xy + (size_t)s * 10;

@@ -37,7 +37,7 @@ struct EdgeD {
     double nx, ny;                  // outward unit normal of the edge v_{i-1} -> v_i
     float vx, vy;                   // v_i
     float len;                      // |v_i - v_{i-1}|
-    float pad;
+    float pad;                      // bits: the record's own index, bank * kMaxHull + i (it travels with staged copies)
 };
 
 // Reach grid: one uint4 per cell.  x / y: bit i set <=> edge i of bank 0 / 1 comes within max(lidar length, cell

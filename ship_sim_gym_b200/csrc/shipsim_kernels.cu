@@ -122,14 +122,16 @@ constexpr int kHdrIn0 = 1 << 8, kHdrIn1 = 1 << 9, kHdrBig = 1 << 10;
 //   [1+2i]   d, ta, -L*nx, -L*ny        [2+2i]  len, bank (0.f / 1.f), 0, 0
 //   big row (more than kMaxCand candidates; rays are then cast serially by the owner lane):
 //   [1]      x, y, hx, hy               [2]     bits(scen), bits(m0), bits(m1), bits(flags)
-// STAGED: the raw EdgeD record of candidate i has already been copied (cp.async) into row[1+2i], row[2+2i].
+// STAGED: the raw EdgeD record of candidate i has already been copied (cp.async) into row[1+2i], row[2+2i]; the
+// record carries its own index (bank * kMaxHull + edge) in `pad`, so the candidate masks need not be walked again.
 template <bool WITH_SAT, bool STAGED>
 __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, float y, float hx, float hy, float c, float s, int scen,
                                                 const uint4 cell, float4 *row)
 {
     unsigned m0 = cell.x, m1 = cell.y;
     const unsigned near = ((m0 != 0u || (cell.z & 1u)) ? 1u : 0u) | ((m1 != 0u || (cell.z & 2u)) ? 2u : 0u);
-    if (__popc(m0) + __popc(m1) > kMaxCand) {
+    const int ncand = __popc(m0) + __popc(m1);
+    if (ncand > kMaxCand) {
         row[0] = make_float4(c, s, __int_as_float(kHdrBig), 0.f);
         row[1] = make_float4(x, y, hx, hy);
         row[2] = make_float4(__int_as_float(scen), __uint_as_float(m0), __uint_as_float(m1), __uint_as_float(cell.z));
@@ -138,37 +140,39 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
     const float L = p.lidar_len;
     const EdgeD *E = p.edges_d + (size_t)scen * (2 * kMaxHull);
     const double xd = (double)x, yd = (double)y, hxd = (double)hx, hyd = (double)hy;
-    float rx[kShipVerts], ry[kShipVerts];
-    if (WITH_SAT) {
-#pragma unroll
-        for (int j = 0; j < kShipVerts; ++j) {                  // hull vertices relative to the ray origin
-            rx[j] = p.ship_lx[j] * c - p.ship_ly[j] * s - hx;
-            ry[j] = p.ship_lx[j] * s + p.ship_ly[j] * c - hy;
-        }
-    }
-    int n = 0;
     unsigned outm = 0u, sepm = 0u;
-    while (m0 | m1) {
-        int idx;
-        if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
-        const unsigned bbit = idx < kMaxHull ? 1u : 2u;
-        PlaneEval pe;
-        if (STAGED) pe = eval_plane_rec(*reinterpret_cast<const double2 *>(row + 1 + 2 * n), row[2 + 2 * n], xd, yd, hxd, hyd);
-        else pe = eval_plane(E + idx, xd, yd, hxd, hyd);
+#pragma unroll 1
+    for (int n = 0; n < ncand; ++n) {
+        double2 nd;
+        float4 ev;
+        if (STAGED) {
+            nd = *reinterpret_cast<const double2 *>(row + 1 + 2 * n);
+            ev = row[2 + 2 * n];
+        } else {
+            int idx;
+            if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
+            nd = __ldg(reinterpret_cast<const double2 *>(E + idx));
+            ev = __ldg(reinterpret_cast<const float4 *>(E + idx) + 1);
+        }
+        const bool bank1 = __float_as_int(ev.w) >= kMaxHull;
+        const unsigned bbit = bank1 ? 2u : 1u;
+        const PlaneEval pe = eval_plane_rec(nd, ev, xd, yd, hxd, hyd);
         if (pe.d > 0.f) outm |= bbit;
         if (WITH_SAT) {
-            float m = pe.nx * rx[0] + pe.ny * ry[0];
+            // does this bank plane have the whole ship in front of it?  n.(hull vertex j - v_i) = d - n.h + (R^T n).l_j:
+            // the normal is rotated into the body frame, where the hull is constant (vertex 0 is the body origin)
+            const float bnx = pe.nx * c + pe.ny * s, bny = pe.ny * c - pe.nx * s;
+            float m = 0.f;
 #pragma unroll
-            for (int j = 1; j < kShipVerts; ++j) m = fminf(m, pe.nx * rx[j] + pe.ny * ry[j]);
-            if (pe.d + m > 0.f) sepm |= bbit;                   // this bank plane has the whole ship in front of it
+            for (int j = 1; j < kShipVerts; ++j) m = fminf(m, bnx * p.ship_lx[j] + bny * p.ship_ly[j]);
+            if (pe.d - (pe.nx * hx + pe.ny * hy) + m > 0.f) sepm |= bbit;
         }
         row[1 + 2 * n] = make_float4(pe.d, pe.ta, -L * pe.nx, -L * pe.ny);
-        row[2 + 2 * n] = make_float4(pe.len, idx < kMaxHull ? 0.f : 1.f, 0.f, 0.f);
-        ++n;
+        row[2 + 2 * n] = make_float4(pe.len, bank1 ? 1.f : 0.f, 0.f, 0.f);
     }
     // cpShapeSegmentQuery: start point inside the shape => alpha = 0 and `point` stays at the ray end
     const unsigned inm = cell.z & 3u & ~outm;
-    row[0] = make_float4(c, s, __int_as_float(n | (int)(inm << 8)), 0.f);
+    row[0] = make_float4(c, s, __int_as_float(ncand | (int)(inm << 8)), 0.f);
     return near & ~sepm;
 }
 
@@ -223,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
     __shared__ float4 s_scr[NW * EPW * kScr4];  // plane-phase output of every env
     __shared__ float2 s_goal[NW * kGoals * EPW];    // goal centres, [warp][goal][env]: only rewritten on reset
     __shared__ float s_ray[2 * 32];
+    __shared__ unsigned char s_src[NW][32];        // ray pass: compacted list of needy envs per warp
     __shared__ float s_stat[NW][8];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -308,41 +313,42 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
             // rows hold that pose's planes.  Up to three needy envs per pass, lanes 0-9 / 10-19 / 20-29 = their rays.
             const int hz_own = __float_as_int(myscr[0].z);
             const bool big = leader && (hz_own & kHdrBig);
-            unsigned need = __ballot_sync(kFull, leader && (hz_own & 0x3ff) != 0);
+            const bool wants = leader && (hz_own & 0x3ff) != 0;
+            const unsigned need = __ballot_sync(kFull, wants);
             if (HIST == 2) __syncwarp();        // the frame copy has read the old readings before any lane overwrites them
             if (big) ray_query_serial(p, myscr, reinterpret_cast<float *>(s_tile + row0) + CF + 6);
-            while (need) {
-                const int s0 = __ffs(need) - 1;
-                const unsigned n1 = need & (need - 1u);
-                const int s1 = __ffs(n1) - 1;                             // -1 when there is no second env
-                const unsigned n2 = n1 & (n1 - 1u);
-                const int s2 = __ffs(n2) - 1;
-                need = n2 & (n2 - 1u);
-                const int src = rslot == 0 ? s0 : (rslot == 1 ? s1 : (rslot == 2 ? s2 : -1));
-                if (src >= 0) {
-                    const int env = src / G;
-                    const int rw = scr0 + env * kScr4;
-                    const float4 hdr = s_scr[rw];
-                    const float ray_c = s_ray[lane], ray_s = s_ray[32 + lane];
-                    const float dirx = hdr.x * ray_c - hdr.y * ray_s, diry = hdr.y * ray_c + hdr.x * ray_s;
-                    const int hz = __float_as_int(hdr.z);
-                    const int n = hz & 0xff;
-                    float v0 = -1.f, v1 = -1.f;                         // hit distance per bank (< 0: none)
+            if (need) {
+                // needy envs, compacted: entry q of the warp's table = the tile row of the q-th needy env
+                if (wants) s_src[warp][__popc(need & ((1u << lane) - 1u))] = (unsigned char)grp;
+                __syncwarp();
+                const int cnt = __popc(need);
+                const float ray_c = s_ray[lane], ray_s = s_ray[32 + lane];
 #pragma unroll 1
-                    for (int i = 0; i < n; ++i) {   // cpPolyShapeSegmentQuery: later accepted edges overwrite earlier ones
-                        const float4 e0 = s_scr[rw + 1 + 2 * i];
-                        const float2 e1 = *reinterpret_cast<const float2 *>(s_scr + rw + 2 + 2 * i);
-                        float val;
-                        const bool ok = ray_vs_plane(e0.x, e0.y, e0.z, e0.w, e1.x, dirx, diry, L, val);
-                        if (ok && e1.y == 0.f) v0 = val;
-                        if (ok && e1.y != 0.f) v1 = val;
+                for (int q = rslot; q < cnt; q += 3) {          // lanes 30, 31 (rslot 3) only keep the others company
+                    if (rslot < 3) {
+                        const int env = s_src[warp][q];
+                        const int rw = scr0 + env * kScr4;
+                        const float4 hdr = s_scr[rw];
+                        const float dirx = hdr.x * ray_c - hdr.y * ray_s, diry = hdr.y * ray_c + hdr.x * ray_s;
+                        const int hz = __float_as_int(hdr.z);
+                        const int n = hz & 0xff;
+                        float v0 = -1.f, v1 = -1.f;                     // hit distance per bank (< 0: none)
+#pragma unroll 1
+                        for (int i = 0; i < n; ++i) {   // cpPolyShapeSegmentQuery: later accepted edges overwrite earlier ones
+                            const float4 e0 = s_scr[rw + 1 + 2 * i];
+                            const float2 e1 = *reinterpret_cast<const float2 *>(s_scr + rw + 2 + 2 * i);
+                            float val;
+                            const bool ok = ray_vs_plane(e0.x, e0.y, e0.z, e0.w, e1.x, dirx, diry, L, val);
+                            if (ok && e1.y == 0.f) v0 = val;
+                            if (ok && e1.y != 0.f) v1 = val;
+                        }
+                        if (hz & kHdrIn0) v0 = L;       // origin inside the bank: alpha = 0, `point` stays at the ray end
+                        if (hz & kHdrIn1) v1 = L;
+                        // LiDAR.query: the first bank (list order) that reports a hit wins; misses keep the old reading
+                        // (sticky vals, models.py:71)
+                        const float v = v0 >= 0.f ? v0 : v1;
+                        if (v >= 0.f) reinterpret_cast<float *>(s_tile + tile0 + env * ROW4)[CF + 6 + rj] = v;
                     }
-                    if (hz & kHdrIn0) v0 = L;       // origin inside the bank: alpha = 0, `point` stays at the ray end
-                    if (hz & kHdrIn1) v1 = L;
-                    // LiDAR.query: the first bank (list order) that reports a hit wins; misses keep the old reading
-                    // (sticky vals, models.py:71)
-                    const float v = v0 >= 0.f ? v0 : v1;
-                    if (v >= 0.f) reinterpret_cast<float *>(s_tile + tile0 + env * ROW4)[CF + 6 + rj] = v;
                 }
             }
             __syncwarp();                       // the rows have been read: the plane phase may overwrite them
