@@ -130,7 +130,7 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
 {
     unsigned m0 = cell.x, m1 = cell.y;
     const unsigned near = ((m0 != 0u || (cell.z & 1u)) ? 1u : 0u) | ((m1 != 0u || (cell.z & 2u)) ? 2u : 0u);
-    const int ncand = __popc(m0) + __popc(m1);
+    const int ncand = (int)((cell.z >> 8) & 0xffu);
     if (ncand > kMaxCand) {
         row[0] = make_float4(c, s, __int_as_float(kHdrBig), 0.f);
         row[1] = make_float4(x, y, hx, hy);
@@ -356,19 +356,18 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
 
         // ---- the candidate planes of the integrated pose: their raw records are copied global -> shared without
         // passing through registers (cp.async) while the goal tests below run
-        const bool near_any = leader && (cell.x | cell.y | cell.z | cell.w) != 0u;
+        const bool near_any = leader && (cell.x | cell.y | (cell.z & 3u)) != 0u;
         // (only worth it when many warps share an SM: with G > 1 the batch is small and the copy would sit on the critical path)
-        const bool staged = G == 1 && near_any && (__popc(cell.x) + __popc(cell.y) <= kMaxCand);
+        const bool staged = G == 1 && near_any && ((cell.z >> 8) & 0xffu) <= (unsigned)kMaxCand;
         if (staged) {
-            const EdgeD *E = p.edges_d + (size_t)r.scen * (2 * kMaxHull);
-            unsigned m0 = cell.x, m1 = cell.y;
-            int n = 0;
-            while (m0 | m1) {
-                int idx;
-                if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
-                cp_async16(myscr + 1 + 2 * n, E + idx);
-                cp_async16(myscr + 2 + 2 * n, reinterpret_cast<const float4 *>(E + idx) + 1);
-                ++n;
+            const float4 *E4 = reinterpret_cast<const float4 *>(p.edges_d + (size_t)r.scen * (2 * kMaxHull));
+#pragma unroll
+            for (int n = 0; n < kMaxCand; ++n) {
+                const unsigned idx = (cell.w >> (8 * n)) & 0xffu;
+                if (idx != 0xffu) {
+                    cp_async16(myscr + 1 + 2 * n, E4 + 2 * idx);
+                    cp_async16(myscr + 2 + 2 * n, E4 + 2 * idx + 1);
+                }
             }
         }
 
@@ -380,28 +379,59 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
             // only goals inside the circle are rotated into the body frame for the exact circle-vs-hull test.
             float2 g[kGoals];
             float gd2[kGoals];
-            unsigned cand = 0u;
 #pragma unroll
             for (int i = 0; i < kGoals; ++i) {
                 g[i] = s_goal[goal0 + i * EPW];
                 const float ux = g[i].x - r.x, uy = g[i].y - r.y;
                 gd2[i] = ux * ux + uy * uy;
-                if (valid && ((r.alive >> i) & 1) && gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
             }
-            while (cand) {
-                const int i = __ffs(cand) - 1;
-                cand &= cand - 1u;
-                float ux = g[0].x, uy = g[0].y;
+            if (G == 1) {
+                // throughput-bound batches: nearest alive goal first (needed for the frame anyway); nothing can touch the
+                // hull unless that one is inside the bounding circle
+                float best = 3.0e38f;
 #pragma unroll
-                for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
-                ux -= r.x; uy -= r.y;
-                const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
-                if (!goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << i); }
+                for (int i = 0; i < kGoals; ++i)
+                    if (((r.alive >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
+                if (valid && best <= p.goal_cull_r2) {           // rare: some goal is within reach of the hull
+#pragma unroll 1
+                    for (int i = 0; i < kGoals; ++i) {
+                        if (!((r.alive >> i) & 1)) continue;
+                        float ux = g[0].x, uy = g[0].y, dd = gd2[0];
+#pragma unroll
+                        for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; dd = gd2[j]; }
+                        if (dd > p.goal_cull_r2) continue;
+                        ux -= r.x; uy -= r.y;
+                        const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
+                        if (!goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << i); }
+                    }
+                    if (goal_reached) {                         // the nearest REMAINING goal goes into the frame
+                        best = 3.0e38f; gx = -1.f; gy = -1.f;
+#pragma unroll
+                        for (int i = 0; i < kGoals; ++i)
+                            if (((r.alive >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
+                    }
+                }
+            } else {
+                // latency-bound batches: independent per-goal culls (no dependent chain before the branch)
+                unsigned cand = 0u;
+#pragma unroll
+                for (int i = 0; i < kGoals; ++i)
+                    if (valid && ((r.alive >> i) & 1) && gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
+                while (cand) {
+                    const int i = __ffs(cand) - 1;
+                    cand &= cand - 1u;
+                    float ux = g[0].x, uy = g[0].y;
+#pragma unroll
+                    for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
+                    ux -= r.x; uy -= r.y;
+                    const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
+                    if (!goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << i); }
+                }
+                float best = 3.0e38f;
+#pragma unroll
+                for (int i = 0; i < kGoals; ++i)
+                    if (((r.alive >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
             }
-            float best = 3.0e38f;
-#pragma unroll
-            for (int i = 0; i < kGoals; ++i)
-                if (((r.alive >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
         }
 
         // ---- plane phase at the integrated pose: next step's lidar planes + this step's ship-vs-bank pre-test
@@ -603,7 +633,7 @@ __global__ void __launch_bounds__(128) build_spawn_rows_kernel(const __grid_cons
     for (int i = 0; i < kScr4; ++i) row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float hx = 0.5f * (p.ship_aabb[2] - p.ship_aabb[0]), hy = 0.5f * (p.ship_aabb[3] - p.ship_aabb[1]);
     const uint4 cell = load_cell(p, sidx, p.spawn_x + hx, p.spawn_y + hy);
-    if ((cell.x | cell.y | cell.z | cell.w) != 0u) plane_phase<false, false>(p, p.spawn_x, p.spawn_y, hx, hy, 1.f, 0.f, sidx, cell, row);
+    if ((cell.x | cell.y | (cell.z & 3u)) != 0u) plane_phase<false, false>(p, p.spawn_x, p.spawn_y, hx, hy, 1.f, 0.f, sidx, cell, row);
     else row[0] = make_float4(1.f, 0.f, 0.f, 0.f);
 }
 
@@ -686,7 +716,16 @@ __global__ void __launch_bounds__(256) build_grid_kernel(const double *hull_xy, 
             if (border) masks[b] = n >= 32 ? kFull : ((1u << n) - 1u);      // unbounded cell: the inside test needs every plane
         }
     }
-    grid[t] = make_uint4(masks[0], masks[1], flags, 0u);
+    // w: the first (up to) four candidates as bytes, bank * kMaxHull + edge, in the order the plane phase evaluates them
+    // (bank 0 first, ascending edge index); 0xff = none.  z bits 8..15: the number of candidates.
+    unsigned list = 0xffffffffu;
+    int cnt = 0;
+    for (int b = 0; b < 2; ++b)
+        for (unsigned m = masks[b]; m; m &= m - 1u) {
+            if (cnt < 4) list = (list & ~(0xffu << (8 * cnt))) | ((unsigned)(b * kMaxHull + (__ffs(m) - 1)) << (8 * cnt));
+            ++cnt;
+        }
+    grid[t] = make_uint4(masks[0], masks[1], flags | ((unsigned)cnt << 8), list);
 }
 
 // ------------------------------------------------------------------------------------------------------------
