@@ -265,3 +265,32 @@ def test_reference_intents_and_errors():
     b.reset()
     with pytest.raises(AssertionError):
         b.step(torch.tensor([0, 1, 2, 3]))
+
+
+@pytest.mark.parametrize("lanes", [1, 8])
+def test_many_candidate_planes_serial_path(lanes):
+    """Banks with 28-32 short edges (regular polygons): a reach-grid cell then names more candidate planes than a
+    shared-memory scratch row holds, which takes the serial lidar path and the full separating-axis pass."""
+    W = H = 600
+    n, K = 2048, 12
+    ang0 = np.linspace(0, 2 * np.pi, 28, endpoint=False)
+    ang1 = np.linspace(0, 2 * np.pi, 32, endpoint=False) + 0.05
+    h0 = np.stack([150 + 110 * np.cos(ang0), 300 + 110 * np.sin(ang0)], 1)       # CCW "islands" inside the map
+    h1 = np.stack([450 + 90 * np.cos(ang1), 280 + 90 * np.sin(ang1)], 1)
+    goals = np.array([[300, 100], [300, 200], [300, 300], [300, 400], [300, 500]], dtype=np.float64)
+    bank = pack_bank([(h0, h1)], [goals])
+    bank["hull_xy"] = bank["hull_xy"].astype(np.float32).astype(np.float64)
+    env, orc = _make_pair(n, bank, W, H, 10, 2, auto_reset=True, seed=3, lanes=lanes)
+    env.reset()
+    orc.reset()
+    rng = np.random.RandomState(5)
+    st = parity.f32_inputs(*parity.random_states(rng, n, W, H, 1, bank["goals"], near=(bank["hull_xy"], bank["hull_n"])))
+    env.set_state(*st)
+    parity.load_oracle_state(orc, *st)
+    acts = rng.randint(0, 3, (K, n)).astype(np.int32)
+    obs, rew, done = _np(*env.rollout(torch.tensor(acts, device=env.device)))
+    ref = orc.step(acts)
+    rep = parity.compare_steps(ref, obs, rew, done, margin_thr=5e-3, label="islands")
+    assert rep["excluded_frac"] < 0.1, rep
+    assert (ref["flags"] & oracle.FLAG_COLLIDING).any() and (orc.lidar[:, :10] >= 0).mean() > 0.1
+    env.close()
