@@ -196,11 +196,11 @@ extern "C" int shipsim_create(const shipsim_config *cfg, int device, shipsim_t *
     if (cfg->lanes_per_env) {
         h->lanes = cfg->lanes_per_env;
     } else {
-        // Auto: small batches are latency bound, so spend lanes on intra-env parallelism until the grid offers
-        // about kTargetWarps warps (148 SMs x 4 schedulers x a few warps each); large batches use one lane per env.
-        const long long kTargetWarps = 148LL * 4 * 6;
-        int g = 32;
-        while (g > 1 && (long long)cfg->num_envs * g / 32 > kTargetWarps) g >>= 1;
+        // Auto (measured on B200, profiles/r01_c_sweep_envs_x_lanes.log): batches that fill the machine are issue bound
+        // and run one lane per env; small batches are latency bound, so lanes are spent on the cooperative passes --
+        // but not beyond 8 per env, since every lane of a group repeats the env's scalar work.
+        const int n = cfg->num_envs;
+        const int g = n < 8192 ? 8 : (n < 24576 ? 4 : (n < 49152 ? 2 : 1));
         h->lanes = g;
     }
     *out = h;

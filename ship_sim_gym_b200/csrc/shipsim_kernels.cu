@@ -122,11 +122,11 @@ constexpr int kHdrIn0 = 1 << 8, kHdrIn1 = 1 << 9, kHdrBig = 1 << 10;
 //   [1+2i]   d, ta, -L*nx, -L*ny        [2+2i]  len, bank (0.f / 1.f), 0, 0
 //   big row (more than kMaxCand candidates; rays are then cast serially by the owner lane):
 //   [1]      x, y, hx, hy               [2]     bits(scen), bits(m0), bits(m1), bits(flags)
-// STAGED: the raw EdgeD record of candidate i has already been copied (cp.async) into row[1+2i], row[2+2i]; the
+// STAGED: the raw EdgeD record of candidate i has already been copied (cp.async) into raw[2i], raw[2i+1]; the
 // record carries its own index (bank * kMaxHull + edge) in `pad`, so the candidate masks need not be walked again.
 template <bool WITH_SAT, bool STAGED>
 __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, float y, float hx, float hy, float c, float s, int scen,
-                                                const uint4 cell, float4 *row)
+                                                const uint4 cell, float4 *row, const float4 *raw = nullptr)
 {
     unsigned m0 = cell.x, m1 = cell.y;
     const unsigned near = ((m0 != 0u || (cell.z & 1u)) ? 1u : 0u) | ((m1 != 0u || (cell.z & 2u)) ? 2u : 0u);
@@ -146,8 +146,8 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
         double2 nd;
         float4 ev;
         if (STAGED) {
-            nd = *reinterpret_cast<const double2 *>(row + 1 + 2 * n);
-            ev = row[2 + 2 * n];
+            nd = *reinterpret_cast<const double2 *>(raw + 2 * n);
+            ev = raw[2 * n + 1];
         } else {
             int idx;
             if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
@@ -228,6 +228,11 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
     __shared__ float2 s_goal[NW * kGoals * EPW];    // goal centres, [warp][goal][env]: only rewritten on reset
     __shared__ float s_ray[2 * 32];
     __shared__ unsigned char s_src[NW][32];        // ray pass: compacted list of needy envs per warp
+    // Raw candidate-plane records (cp.async targets).  With G > 1 (few envs per CTA) they get their own area and are
+    // requested at the top of the iteration; with G = 1 that would cost 16 KB, so they land in the scratch row itself
+    // once the ray pass has finished with it.
+    constexpr int RAW4 = G > 1 ? NW * EPW * 2 * kMaxCand : 1;
+    __shared__ float4 s_raw[RAW4];
     __shared__ float s_stat[NW][8];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -242,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
     const int scr0 = warp * EPW * kScr4;         // this warp's scratch rows
     const int my0 = scr0 + grp * kScr4;
     const int goal0 = warp * kGoals * EPW + grp;  // + g * EPW
+    const int raw0 = G > 1 ? (warp * EPW + grp) * 2 * kMaxCand : 0;
 #define row4 (s_tile + row0)
 #define myscr (s_scr + my0)
 #define stat (s_stat[warp])
@@ -297,6 +303,21 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
     for (int k = -1; k < p.K; ++k) {
         const bool live = k >= 0;
         float dvx = 0.f, dvy = 0.f, dw = 0.f;
+        // the candidate planes of the integrated pose: their raw records are copied global -> shared without passing
+        // through registers (cp.async), in the background
+        const bool near_any = leader && (cell.x | cell.y | (cell.z & 3u)) != 0u;
+        const bool staged = near_any && ((cell.z >> 8) & 0xffu) <= (unsigned)kMaxCand;
+        if (G > 1 && staged) {
+            const float4 *E4 = reinterpret_cast<const float4 *>(p.edges_d + (size_t)r.scen * (2 * kMaxHull));
+#pragma unroll
+            for (int n = 0; n < kMaxCand; ++n) {
+                const unsigned idx = (cell.w >> (8 * n)) & 0xffu;
+                if (idx != 0xffu) {
+                    cp_async16(s_raw + raw0 + 2 * n, E4 + 2 * idx);
+                    cp_async16(s_raw + raw0 + 2 * n + 1, E4 + 2 * idx + 1);
+                }
+            }
+        }
         if (live) {
             const int a = a_next;
             ap += act_stride;
@@ -354,12 +375,7 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
             __syncwarp();                       // the rows have been read: the plane phase may overwrite them
         }
 
-        // ---- the candidate planes of the integrated pose: their raw records are copied global -> shared without
-        // passing through registers (cp.async) while the goal tests below run
-        const bool near_any = leader && (cell.x | cell.y | (cell.z & 3u)) != 0u;
-        // (only worth it when many warps share an SM: with G > 1 the batch is small and the copy would sit on the critical path)
-        const bool staged = G == 1 && near_any && ((cell.z >> 8) & 0xffu) <= (unsigned)kMaxCand;
-        if (staged) {
+        if (G == 1 && staged) {                 // G = 1: into the scratch row, now that the ray pass is done with it
             const float4 *E4 = reinterpret_cast<const float4 *>(p.edges_d + (size_t)r.scen * (2 * kMaxHull));
 #pragma unroll
             for (int n = 0; n < kMaxCand; ++n) {
@@ -435,10 +451,10 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
         }
 
         // ---- plane phase at the integrated pose: next step's lidar planes + this step's ship-vs-bank pre-test
-        if (G == 1) cp_async_wait_all();
+        cp_async_wait_all();
         unsigned ask = 0u;
         if (leader) {
-            if (staged) ask = plane_phase<true, true>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, myscr);
+            if (staged) ask = plane_phase<true, true>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, myscr, G > 1 ? s_raw + raw0 : myscr + 1);
             else if (near_any) ask = plane_phase<true, false>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, myscr);
             else myscr[0] = make_float4(c, s, 0.f, 0.f);
         }
@@ -786,10 +802,15 @@ static cudaError_t launch_g(const StepParams &p, cudaStream_t stream, LaunchShap
     const int envs_per_cta = kThreads / G;
     const int blocks = (p.N + envs_per_cta - 1) / envs_per_cta;
     if (shape) { shape->lanes_per_env = G; shape->threads = kThreads; shape->blocks = blocks; }
-    if (G == 1 && blocks >= 148 * 8) {
-        if (p.history == 2) step_kernel<G, 2, 5><<<blocks, kThreads, 0, stream>>>(p);
-        else step_kernel<G, 1, 5><<<blocks, kThreads, 0, stream>>>(p);
-    } else {
+    bool launched = false;
+    if constexpr (G == 1) {
+        if (blocks >= 148 * 8) {
+            if (p.history == 2) step_kernel<G, 2, 5><<<blocks, kThreads, 0, stream>>>(p);
+            else step_kernel<G, 1, 5><<<blocks, kThreads, 0, stream>>>(p);
+            launched = true;
+        }
+    }
+    if (!launched) {
         if (p.history == 2) step_kernel<G, 2, SHIPSIM_MIN_BLOCKS><<<blocks, kThreads, 0, stream>>>(p);
         else step_kernel<G, 1, SHIPSIM_MIN_BLOCKS><<<blocks, kThreads, 0, stream>>>(p);
     }
