@@ -117,6 +117,11 @@ int shipsim_destroy(shipsim_t *h);
 int shipsim_load_scenarios(shipsim_t *h, const double *host_hull_xy, const int32_t *host_hull_n,
                            const double *host_goals_xy, int32_t n_scenarios, int32_t maxv);
 
+/* Curriculum knob (ship_gym/curriculum.py:23-50 is meant to schedule scalars such as EnvConfig.MAX_STEPS, config.py:16):
+ * change the episode length cap of a live handle.  Takes effect from the next shipsim_step; envs whose step count is
+ * already at or beyond the new cap end on their next step, exactly as ShipEnv.is_done would (ship_env.py:131). */
+int shipsim_set_max_steps(shipsim_t *h, int32_t max_steps);
+
 /* Per-env state lives in ONE caller-owned device buffer of shipsim_state_bytes() bytes, laid out as
  * SHIPSIM_STATE_PLANES planes of float4[num_envs] (structure of arrays, 128 B per env):
  *   0: x, y, angle, vx          1: vy, w, episode_return, bits{rudder/5+2 | alive<<3 | step_count<<8}

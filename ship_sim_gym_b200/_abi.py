@@ -20,7 +20,7 @@ SYMBOLS = (
     "shipsim_abi_version", "shipsim_last_error", "shipsim_config_default", "shipsim_create", "shipsim_destroy",
     "shipsim_load_scenarios", "shipsim_state_bytes", "shipsim_stats_bytes", "shipsim_bind_state", "shipsim_reset",
     "shipsim_step", "shipsim_step_host", "shipsim_stats_read", "shipsim_set_state", "shipsim_get_state",
-    "shipsim_launch_count", "shipsim_launch_shape",
+    "shipsim_launch_count", "shipsim_launch_shape", "shipsim_set_max_steps",
 )
 
 
@@ -72,6 +72,7 @@ def load():
     L.shipsim_stats_read.argtypes = [vp, vp, C.c_int, vp]
     L.shipsim_set_state.argtypes = [vp, vp, vp, vp, vp, vp]
     L.shipsim_get_state.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.shipsim_set_max_steps.argtypes = [vp, i32]
     L.shipsim_launch_count.argtypes = [vp, C.POINTER(i64)]
     L.shipsim_launch_shape.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     for name in SYMBOLS:

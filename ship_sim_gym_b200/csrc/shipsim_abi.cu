@@ -315,6 +315,15 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
     return SHIPSIM_OK;
 }
 
+extern "C" int shipsim_set_max_steps(shipsim_t *h, int32_t max_steps)
+{
+    if (!h) return fail(SHIPSIM_ERR_ARG, "handle is NULL");
+    if (max_steps < 1 || max_steps >= (1 << 22)) return fail(SHIPSIM_ERR_ARG, "need 1 <= max_steps < 2^22");
+    h->cfg.max_steps = max_steps;
+    h->p.max_steps = max_steps;
+    return SHIPSIM_OK;
+}
+
 extern "C" size_t shipsim_state_bytes(const shipsim_t *h) { return h ? (size_t)h->cfg.num_envs * kPlanes * sizeof(float4) : 0; }
 extern "C" size_t shipsim_stats_bytes(const shipsim_t *) { return (size_t)kStatSlots * kStatLen * sizeof(double); }
 

@@ -162,6 +162,11 @@ class BatchedShipEnv(object):
         _abi.check(self.L.shipsim_load_scenarios(self._h, bank.hull_xy.ctypes.data, bank.hull_n.ctypes.data,
                                                  bank.goals.ctypes.data, len(bank), bank.maxv))
 
+    def set_max_steps(self, max_steps):
+        """Change EnvConfig.MAX_STEPS (config.py:16) of the live batch -- a curriculum knob."""
+        _abi.check(self.L.shipsim_set_max_steps(self._h, int(max_steps)))
+        self.knobs["max_steps"] = int(max_steps)
+
     def seed(self, seed=None):
         """ship_env.py:52-60 seeds numpy only; here it also re-keys the action-space sampler."""
         if seed is None:

@@ -126,3 +126,27 @@ def test_policy_rollout_graph_replay_matches_eager():
         first = obs[1:, :, :16].cpu().numpy()
         d = done.cpu().numpy().astype(bool)
         assert ((first == -1).all(-1) == d).all()                 # the older frame is all -1 exactly on reset steps
+
+
+def test_curriculum_driver_on_a_live_batch():
+    """EnvConfig.MAX_STEPS as a curriculum knob: the cap changes on the live handle (shipsim_set_max_steps) and the
+    time-out statistics follow it."""
+    from ship_sim_gym_b200 import BatchedShipEnv, Curriculum, CurriculumDriver
+    n = 1024
+    env = BatchedShipEnv(n, bank=_bank(), seed=0)
+    cur = Curriculum([5, 12], [-10.0], repeat_condition=0)            # any mean return > -10 passes
+    drv = CurriculumDriver(env, cur, knob="max_steps", min_episodes=n)
+    env.reset()
+    idle = torch.ones(8, n, dtype=torch.int32, device=env.device)     # rudder only: nobody moves, episodes only time out
+    obs, rew, done = env.rollout(idle)
+    assert done[4].all() and done.sum() == n                          # MAX_STEPS = 5 (ship_env.py:131)
+    s = env.stats()
+    assert s["timeout"] == n and s["length_sum"] == 5 * n
+    adv, mean = drv.update()
+    assert adv and mean == pytest.approx(-0.05) and int(cur) == 12
+    obs, rew, done = env.rollout(torch.ones(15, n, dtype=torch.int32, device=env.device))
+    # 3 steps of the running episode were done under the old cap; it now ends at step count 12
+    assert done[8].all() and done.sum() == n
+    with pytest.raises(ValueError):
+        env.set_max_steps(0)
+    env.close()

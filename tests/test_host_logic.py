@@ -60,3 +60,57 @@ def test_space_stand_ins():
     assert all(0 <= d.sample() < 3 for _ in range(50))
     b = Box(0, 600, (32,), np.uint8)                                  # ship_env.py:48
     assert b.shape == (32,) and b.high.max() == 600 and b.dtype == np.uint8
+
+
+class _FakeEnv(object):
+    """Duck-typed stand-in for BatchedShipEnv: what CurriculumDriver touches."""
+
+    def __init__(self):
+        import torch
+        self.t = torch.zeros(16, dtype=torch.float64)
+        self.max_steps = None
+        self.loaded = []
+
+    def stats_tensor(self, clear=False):
+        out = self.t.clone()
+        if clear:
+            self.t.zero_()
+        return out
+
+    def set_max_steps(self, n):
+        self.max_steps = n
+
+    def load_scenarios(self, bank):
+        self.loaded.append(bank)
+
+    def finish(self, episodes, mean_return):
+        self.t[0] += episodes
+        self.t[1] += episodes * mean_return
+
+
+def test_curriculum_driver_schedules_max_steps_and_bank_tiers():
+    pytest.importorskip("torch")
+    env = _FakeEnv()
+    cur = curriculum.Curriculum([100, 300, 1000], [-0.5, 0.5], repeat_condition=0)
+    drv = curriculum.CurriculumDriver(env, cur, knob="max_steps", min_episodes=10)
+    assert env.max_steps == 100                                   # lesson 0 applied at construction
+    env.finish(5, 1.0)
+    assert drv.update() == (False, None)                          # too few episodes: statistics keep accumulating
+    env.finish(5, 1.0)
+    adv, mean = drv.update()
+    assert adv and mean == pytest.approx(1.0) and env.max_steps == 300
+    assert float(env.t[0]) == 0.0                                 # statistics were consumed
+    env.finish(20, 0.2)
+    assert drv.update() == (False, pytest.approx(0.2)) and env.max_steps == 300
+    env.finish(20, 0.9)
+    assert drv.update()[0] and env.max_steps == 1000
+    # the all-reduce hook sees the vector of this rank and returns the global one
+    env2 = _FakeEnv()
+    drv2 = curriculum.CurriculumDriver(env2, curriculum.Curriculum([0, 1], [0.0], repeat_condition=0), knob="bank",
+                                       banks=["easy", "hard"], all_reduce=lambda t: t * 2)
+    assert env2.loaded == ["easy"]
+    env2.finish(4, 0.5)
+    adv, mean = drv2.update()
+    assert adv and mean == pytest.approx(0.5) and env2.loaded == ["easy", "hard"]
+    with pytest.raises(ValueError):
+        curriculum.CurriculumDriver(env2, cur, knob="bank")
