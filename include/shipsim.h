@@ -117,6 +117,18 @@ int shipsim_destroy(shipsim_t *h);
 int shipsim_load_scenarios(shipsim_t *h, const double *host_hull_xy, const int32_t *host_hull_n,
                            const double *host_goals_xy, int32_t n_scenarios, int32_t maxv);
 
+/* The same level data generated ON THE DEVICE, replacing the host loop over ShipGame.reset() calls: per scenario
+ * game_map.gen_river_poly (game_map.py:22-73; map_N segments per bank, bank width = width_frac * W / 2), pm.Poly's
+ * convex hull (models.py:180) and ShipGame.gen_goal_path (game.py:300-330), in double precision, then the packing,
+ * reach grid and spawn rows shipsim_load_scenarios derives.  Draws come from Philox4x32-10 keyed by (seed, scenario):
+ * the distributions are the reference's, the individual maps are not (CPython's Mersenne Twister cannot be matched).
+ * Work is enqueued on `stream`; the call waits for it (a 4-byte read-back sizes the SAT pass). */
+int shipsim_generate_scenarios(shipsim_t *h, int32_t n_scenarios, uint64_t seed, int32_t map_N, float width_frac, void *stream);
+
+/* Read the device-generated bank back (validation / inspection): host_hull_xy[n][2][SHIPSIM_MAX_HULL][2] (CCW, zero
+ * padded), host_hull_n[n][2], host_goals[n][5][2]; hull vertices are the fp32-rounded ones the kernels use. */
+int shipsim_read_scenarios(shipsim_t *h, double *host_hull_xy, int32_t *host_hull_n, double *host_goals);
+
 /* Curriculum knob (ship_gym/curriculum.py:23-50 is meant to schedule scalars such as EnvConfig.MAX_STEPS, config.py:16):
  * change the episode length cap of a live handle.  Takes effect from the next shipsim_step; envs whose step count is
  * already at or beyond the new cap end on their next step, exactly as ShipEnv.is_done would (ship_env.py:131). */

@@ -21,6 +21,9 @@ struct shipsim_handle {
     EdgeD *d_edges = nullptr;
     uint4 *d_grid = nullptr;
     float4 *d_spawn = nullptr;
+    double *d_gen_xy = nullptr, *d_gen_goals = nullptr;   // raw output of the device scenario generator (for read-back)
+    int *d_gen_n = nullptr;
+    int gen_count = 0;
     int lanes = 1;
     // staging for shipsim_step_host (allocated on first use, sized for the largest K seen)
     int32_t *d_act = nullptr; float *d_obs = nullptr; float *d_rew = nullptr; uint8_t *d_done = nullptr;
@@ -213,7 +216,8 @@ extern "C" int shipsim_destroy(shipsim_t *h)
     DeviceGuard g(h->device);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto &ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
-    cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_spawn); cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
+    cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_spawn); cudaFree(h->d_act);
+    cudaFree(h->d_gen_xy); cudaFree(h->d_gen_goals); cudaFree(h->d_gen_n); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
     delete h;
     return SHIPSIM_OK;
 }
@@ -301,7 +305,7 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
     if (e == cudaSuccess) {
         // plane phase at the spawn pose of every scenario (what an env that is reset inside the kernel starts from)
         StepParams q = h->p;
-        q.bank = d; q.edges_d = de; q.grid = dg; q.n_scen = n_scen; q.maxv = dev_maxv; q.scen_stride4 = stride4;
+        q.bank = d; q.edges_d = de; q.grid = dg; q.n_scen = n_scen; q.maxv = dev_maxv; q.scen_stride4 = stride4; q.hull_max = dev_maxv;
         e = launch_build_spawn_rows(q, dsp, 0);
     }
     if (e == cudaSuccess) e = cudaDeviceSynchronize();           // also: no launch may still be reading the old bank
@@ -310,8 +314,77 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
     cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_spawn);
     h->d_bank = d; h->d_edges = de; h->d_grid = dg; h->d_spawn = dsp;
     h->p.bank = d; h->p.edges_d = de; h->p.grid = dg; h->p.spawn_rows = dsp;
-    h->p.n_scen = n_scen; h->p.maxv = dev_maxv; h->p.scen_stride4 = stride4;
+    h->p.n_scen = n_scen; h->p.maxv = dev_maxv; h->p.scen_stride4 = stride4; h->p.hull_max = dev_maxv;
     h->launches += 2;
+    return SHIPSIM_OK;
+}
+
+// ---- scenario generation on the device ------------------------------------------------------
+extern "C" int shipsim_generate_scenarios(shipsim_t *h, int32_t n_scen, uint64_t seed, int32_t map_N, float width_frac, void *stream)
+{
+    if (!h) return fail(SHIPSIM_ERR_ARG, "handle is NULL");
+    if (n_scen < 1 || n_scen >= (1 << 28)) return fail(SHIPSIM_ERR_ARG, "n_scenarios out of range");
+    if (map_N < 1 || map_N > kMaxHull - 2) return fail(SHIPSIM_ERR_ARG, "map_N must be in [1, 30] (two wall corners are added; hulls hold 32 vertices)");
+    if (!(width_frac > 0.f) || !(width_frac <= 1.f)) return fail(SHIPSIM_ERR_ARG, "width_frac must be in (0, 1]");
+    DeviceGuard g(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int maxv = kMaxHull, stride4 = kBankHeader4 + 2 * maxv;
+    float4 *d = nullptr, *dsp = nullptr;
+    EdgeD *de = nullptr;
+    uint4 *dg = nullptr;
+    double *dxy = nullptr, *dgo = nullptr;
+    int *dn = nullptr, *dmax = nullptr;
+    auto cleanup = [&]() { cudaFree(d); cudaFree(de); cudaFree(dg); cudaFree(dsp); cudaFree(dxy); cudaFree(dgo); cudaFree(dn); cudaFree(dmax); };
+    cudaError_t e = cudaMalloc(&d, (size_t)n_scen * stride4 * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&de, (size_t)n_scen * 2 * kMaxHull * sizeof(EdgeD));
+    if (e == cudaSuccess) e = cudaMalloc(&dg, (size_t)n_scen * kGridN * kGridN * sizeof(uint4));
+    if (e == cudaSuccess) e = cudaMalloc(&dsp, (size_t)n_scen * (1 + 2 * 4) * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&dxy, (size_t)n_scen * 2 * kMaxHull * 2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&dgo, (size_t)n_scen * 10 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&dn, (size_t)n_scen * 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&dmax, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d, 0, (size_t)n_scen * stride4 * sizeof(float4), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(de, 0, (size_t)n_scen * 2 * kMaxHull * sizeof(EdgeD), s);
+    if (e == cudaSuccess) e = launch_gen_scenarios(seed, n_scen, h->cfg.bounds_w, h->cfg.bounds_h, map_N, width_frac, dxy, dn, dgo, s);
+    if (e == cudaSuccess) e = launch_max_hull(dn, n_scen * 2, dmax, s);
+    if (e == cudaSuccess) e = launch_pack_bank(dxy, dn, dgo, n_scen, maxv, stride4, d, de, s);
+    if (e == cudaSuccess) {
+        const double pad = -(double)h->p.gridp.x0;
+        const double cw = ((double)h->cfg.bounds_w + 2.0 * pad) / kGridN, ch = ((double)h->cfg.bounds_h + 2.0 * pad) / kGridN;
+        const double margin = 0.05 + 1e-4 * std::max((double)h->cfg.bounds_w, (double)h->cfg.bounds_h);
+        const double reach = std::max((double)h->cfg.lidar_distance, std::sqrt(cw * cw + ch * ch)) + margin;
+        e = launch_build_grid(dxy, dn, n_scen, kMaxHull, (double)h->p.gridp.x0, (double)h->p.gridp.y0, cw, ch, reach, margin, dg, s);
+    }
+    int hull_max = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&hull_max, dmax, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);          // 4-byte read-back: the SAT pass lane layout depends on it
+    if (e == cudaSuccess) {
+        StepParams q = h->p;
+        q.bank = d; q.edges_d = de; q.grid = dg; q.n_scen = n_scen; q.maxv = maxv; q.scen_stride4 = stride4; q.hull_max = hull_max;
+        e = launch_build_spawn_rows(q, dsp, s);
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();            // no launch may still be reading the old bank
+    if (e != cudaSuccess) { cleanup(); return fail(SHIPSIM_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaFree(dmax);
+    cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_spawn);
+    cudaFree(h->d_gen_xy); cudaFree(h->d_gen_goals); cudaFree(h->d_gen_n);
+    h->d_bank = d; h->d_edges = de; h->d_grid = dg; h->d_spawn = dsp;
+    h->d_gen_xy = dxy; h->d_gen_goals = dgo; h->d_gen_n = dn; h->gen_count = n_scen;
+    h->p.bank = d; h->p.edges_d = de; h->p.grid = dg; h->p.spawn_rows = dsp;
+    h->p.n_scen = n_scen; h->p.maxv = maxv; h->p.scen_stride4 = stride4; h->p.hull_max = hull_max;
+    h->launches += 5;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_read_scenarios(shipsim_t *h, double *host_hull_xy, int32_t *host_hull_n, double *host_goals)
+{
+    if (!h || !host_hull_xy || !host_hull_n || !host_goals) return fail(SHIPSIM_ERR_ARG, "NULL argument");
+    if (!h->d_gen_xy) return fail(SHIPSIM_ERR_STATE, "no device-generated bank: call shipsim_generate_scenarios first");
+    DeviceGuard g(h->device);
+    const size_t S = (size_t)h->gen_count;
+    CU(cudaMemcpy(host_hull_xy, h->d_gen_xy, S * 2 * kMaxHull * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(host_hull_n, h->d_gen_n, S * 2 * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(host_goals, h->d_gen_goals, S * 10 * sizeof(double), cudaMemcpyDeviceToHost));
     return SHIPSIM_OK;
 }
 

@@ -73,7 +73,8 @@ struct StepParams {
     long long env_id_offset;
     int N, K;
     int action_dtype, history, auto_reset, max_steps;
-    int n_scen, maxv, scen_stride4;
+    int n_scen, maxv, scen_stride4;   // maxv = edge stride of the fp32 records
+    int hull_max;                     // largest hull in the bank (SAT pass lane layout)
     unsigned step0;              // global step counter at launch (random-action stream)
     float W, H, dt, damping;
     float lidar_len;

@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
         s_ray[32 + threadIdx.x] = p.ray_s[threadIdx.x % kBeams];
     }
     if (lane < 8) stat[lane] = 0.f;
-    const int lps_sh = p.maxv <= 8 ? 3 : (p.maxv <= 16 ? 4 : 5);    // SAT pass: log2(lanes per env slot)
+    const int lps_sh = p.hull_max <= 8 ? 3 : (p.hull_max <= 16 ? 4 : 5);    // SAT pass: log2(lanes per env slot)
     const int lps = 1 << lps_sh, nslots = 32 >> lps_sh;
     const int sslot = lane >> lps_sh, sel = lane & (lps - 1);
     const unsigned slotmask = lps == 32 ? kFull : (((1u << lps) - 1u) << (sslot * lps));

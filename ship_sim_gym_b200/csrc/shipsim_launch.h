@@ -6,6 +6,7 @@
 namespace shipsim {
 
 struct StepParams;
+struct EdgeD;
 constexpr int kThreads = 128;
 
 struct LaunchShape { int lanes_per_env, threads, blocks; };
@@ -16,6 +17,11 @@ cudaError_t launch_reset(const StepParams &p, const uint8_t *mask, const int *sc
 cudaError_t launch_build_grid(const double *hull_xy, const int *hull_n, int n_scen, int maxv_in, double gx0, double gy0,
                               double cw, double ch, double reach, double touch_margin, uint4 *grid, cudaStream_t stream);
 cudaError_t launch_build_spawn_rows(const StepParams &p, float4 *rows, cudaStream_t stream);
+cudaError_t launch_gen_scenarios(unsigned long long seed, int n_scen, double W, double H, int map_N, double width_frac, double *hull_xy,
+                                 int *hull_n, double *goals, cudaStream_t stream);
+cudaError_t launch_pack_bank(double *hull_xy, const int *hull_n, const double *goals, int n_scen, int maxv, int stride4, float4 *bank,
+                             EdgeD *edges, cudaStream_t stream);
+cudaError_t launch_max_hull(const int *hull_n, int n, int *out, cudaStream_t stream);
 cudaError_t launch_stats_reduce(double *slots, double *out, int clear, cudaStream_t stream);
 
 }  // namespace shipsim

@@ -85,7 +85,7 @@ class BatchedShipEnv(object):
 
     def __init__(self, num_envs, game_config=None, env_config=None, device=None, seed=0, n_scenarios=1024,
                  bank=None, map_N=10, map_width_frac=0.5, auto_reset=True, honour_lidar_config=False,
-                 env_id_offset=0, lanes_per_env=0, validate_actions=True):
+                 env_id_offset=0, lanes_per_env=0, validate_actions=True, scenario_source="host"):
         self.knobs = snapshot(game_config, env_config, honour_lidar_config)
         if self.knobs["lidar"]["N_BEAMS"] != _abi.N_BEAMS:
             raise NotImplementedError("N_BEAMS must be 10")
@@ -94,6 +94,7 @@ class BatchedShipEnv(object):
         if self.device.type != "cuda":
             raise _abi.ShipsimError("BatchedShipEnv needs a CUDA device: there is no CPU fallback")
         self.L = _abi.load()
+        self._needs_reset = True
         self.action_space = Discrete(3)                        # ship_env.py:19
         self.history = self.knobs["history"]
         self.n_states = 2 + 1 + 1 + 2 + _abi.N_BEAMS           # ship_env.py:43
@@ -124,10 +125,17 @@ class BatchedShipEnv(object):
         _abi.check(self.L.shipsim_create(C.byref(cfg), self.device.index or 0, C.byref(self._h)))
         self._obs_dim_kernel = _abi.FRAME * cfg.history
 
-        if bank is None:
-            bank = ScenarioBank.generate(n_scenarios, self.bounds, seed=self.seed_value, map_N=map_N,
-                                         width_frac=map_width_frac)
-        self.load_scenarios(bank)
+        self._n_generated = 0
+        if scenario_source not in ("host", "device"):
+            raise ValueError("scenario_source must be 'host' or 'device'")
+        if bank is None and scenario_source == "device":
+            # maps generated by the GPU itself (shipsim_generate_scenarios): no host loop over resets
+            self.generate_scenarios(n_scenarios, seed=self.seed_value, map_N=map_N, map_width_frac=map_width_frac)
+        else:
+            if bank is None:
+                bank = ScenarioBank.generate(n_scenarios, self.bounds, seed=self.seed_value, map_N=map_N,
+                                             width_frac=map_width_frac)
+            self.load_scenarios(bank)
 
         with torch.cuda.device(self.device):
             nbytes = self.L.shipsim_state_bytes(self._h)
@@ -137,7 +145,6 @@ class BatchedShipEnv(object):
             _abi.check(self.L.shipsim_bind_state(self._h, self.state.data_ptr(), self._stats_slots.data_ptr(), self._stream()))
         self._hist = None
         self.total_steps = 0
-        self._needs_reset = True
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -161,6 +168,30 @@ class BatchedShipEnv(object):
         self.bank = bank
         _abi.check(self.L.shipsim_load_scenarios(self._h, bank.hull_xy.ctypes.data, bank.hull_n.ctypes.data,
                                                  bank.goals.ctypes.data, len(bank), bank.maxv))
+
+    def _gen_count(self):
+        return self._n_generated
+
+    def generate_scenarios(self, n_scenarios, seed=0, map_N=10, map_width_frac=0.5):
+        """Replace the scenario bank by `n_scenarios` maps generated on the device (river banks, hulls, goal paths;
+        SURVEY.md §8 f2).  Envs keep the goals of the scenario they started with until their next reset, so call it
+        where all envs are reset (e.g. followed by `reset()`)."""
+        with torch.cuda.device(self.device):
+            _abi.check(self.L.shipsim_generate_scenarios(self._h, int(n_scenarios), int(seed) & 0xFFFFFFFFFFFFFFFF, int(map_N),
+                                                         float(map_width_frac), self._stream()))
+        self.bank = None
+        self._n_generated = int(n_scenarios)
+        self._needs_reset = True
+
+    def read_scenarios(self):
+        """The device-generated bank as a host ScenarioBank (validation / inspection)."""
+        S = self._gen_count()
+        hull_xy = np.zeros((S, 2, _abi.MAX_HULL, 2))
+        hull_n = np.zeros((S, 2), dtype=np.int32)
+        goals = np.zeros((S, 5, 2))
+        with torch.cuda.device(self.device):
+            _abi.check(self.L.shipsim_read_scenarios(self._h, hull_xy.ctypes.data, hull_n.ctypes.data, goals.ctypes.data))
+        return ScenarioBank(hull_xy, hull_n, goals, self.bounds)
 
     def set_max_steps(self, max_steps):
         """Change EnvConfig.MAX_STEPS (config.py:16) of the live batch -- a curriculum knob."""
