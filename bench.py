@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra (non-headline) configurations")
     ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--window", type=int, default=0, help="steps_in_flight (0 = auto)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "ours" else 0)
 
@@ -191,7 +192,7 @@ def main():
 
     bank = ScenarioBank.generate(N_SCENARIOS, (600, 600), seed=SEED)
     env = BatchedShipEnv(ENVS, bank=bank, seed=SEED, auto_reset=True, device=dev, env_id_offset=rank * ENVS,
-                         lanes_per_env=args.lanes, validate_actions=False)
+                         lanes_per_env=args.lanes, steps_in_flight=args.window, validate_actions=False)
     env.reset()
     gen = torch.Generator(device=dev).manual_seed(SEED + rank)
     actions = torch.randint(0, 3, (ROLLOUT, ENVS), dtype=torch.int32, device=dev, generator=gen)
@@ -294,7 +295,7 @@ def main():
             "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
-            "launch_shape": {k: info[k] for k in ("lanes_per_env", "threads_per_cta", "ctas")},
+            "launch_shape": {k: info[k] for k in ("lanes_per_env", "threads_per_cta", "ctas", "steps_in_flight")},
             "stats": env.stats(), "extra": extra,
         }
         print(json.dumps(line))

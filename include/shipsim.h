@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SHIPSIM_ABI_VERSION 1
+#define SHIPSIM_ABI_VERSION 2
 #define SHIPSIM_N_GOALS 5        /* game.py:17  N_GOALS */
 #define SHIPSIM_N_BEAMS 10       /* models.py:29 LiDAR(n_beams=10): the only beam count the reference ever uses */
 #define SHIPSIM_FRAME 16         /* ship_env.py:43 n_states = 2+1+1+2+n_beams */
@@ -94,7 +94,16 @@ typedef struct shipsim_config {
     float spawn_y;               /* game.py:274 (25); spawn x is bounds_w/2                          */
     int32_t lanes_per_env;       /* cooperating lanes per env: 0 = choose from num_envs, else 1, 2, 4, 8, 16 or 32
                                     (32 = one warp per env, for small latency-bound batches)         */
+    int32_t steps_in_flight;     /* K-step rollouts of small batches: consecutive steps of one env speculated together
+                                    (the rigid-body recurrence is cheap and sequential; lidar, overlap and goal tests
+                                    of different steps run on different lanes; the window is cut at the first `done`).
+                                    0 = choose from num_envs, 1 = off (one step after another), else 4, 8, 16 or 32.
+                                    Results are bit-identical either way.                              */
+    int32_t reserved0;           /* keeps sizeof a multiple of 8; must be 0                           */
 } shipsim_config;
+
+/* num_envs up to which steps_in_flight = 0 selects the time-parallel kernel (measured on B200, profiles/) */
+#define SHIPSIM_WINDOW_AUTO_MAX_ENVS 16384
 
 typedef struct shipsim_handle shipsim_t;
 
@@ -181,6 +190,8 @@ int shipsim_get_state(shipsim_t *h, float *host_pose, int32_t *host_ints, float 
 /* Introspection for benchmarks: launches issued so far, lanes per env and CTA size actually used. */
 int shipsim_launch_count(const shipsim_t *h, int64_t *out);
 int shipsim_launch_shape(const shipsim_t *h, int32_t *lanes_per_env, int32_t *threads_per_cta, int32_t *ctas);
+/* steps of one env the last launch speculated together (1 = the serial-in-time kernel ran) */
+int shipsim_launch_window(const shipsim_t *h, int32_t *steps_in_flight);
 
 #ifdef __cplusplus
 }

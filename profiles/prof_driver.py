@@ -16,6 +16,7 @@ ap.add_argument("--envs", type=int, default=4096)
 ap.add_argument("--K", type=int, default=1000)
 ap.add_argument("--reps", type=int, default=4)
 ap.add_argument("--lanes", type=int, default=0)
+ap.add_argument("--window", type=int, default=0, help="steps_in_flight: 0 auto, 1 serial-in-time kernel, 4/8/16/32 window kernel")
 ap.add_argument("--hard", action="store_true")
 ap.add_argument("--wf", type=float, default=0.5, help="map width_frac (0.01 = banks hug the walls: almost no env is near a bank)")
 ap.add_argument("--presteps", type=int, default=200, help="untimed env-steps first, so envs are spread over their episodes")
@@ -25,10 +26,10 @@ if a.hard:
     class GC(GameConfig):
         BOUNDS = (1000, 1000)
     bank = ScenarioBank.generate(256, (1000, 1000), seed=0, map_N=30, width_frac=0.9)
-    env = BatchedShipEnv(a.envs, GC, EnvConfig, bank=bank, honour_lidar_config=True, lanes_per_env=a.lanes, validate_actions=False)
+    env = BatchedShipEnv(a.envs, GC, EnvConfig, bank=bank, honour_lidar_config=True, lanes_per_env=a.lanes, steps_in_flight=a.window, validate_actions=False)
 else:
     bank = ScenarioBank.generate(1024, (600, 600), seed=0, width_frac=a.wf)
-    env = BatchedShipEnv(a.envs, bank=bank, lanes_per_env=a.lanes, validate_actions=False)
+    env = BatchedShipEnv(a.envs, bank=bank, lanes_per_env=a.lanes, steps_in_flight=a.window, validate_actions=False)
 env.reset()
 acts = torch.randint(0, 3, (a.K, a.envs), dtype=torch.int32, device="cuda")
 out = env.alloc_rollout(a.K)

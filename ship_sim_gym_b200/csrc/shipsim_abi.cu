@@ -25,13 +25,14 @@ struct shipsim_handle {
     int *d_gen_n = nullptr;
     int gen_count = 0;
     int lanes = 1;
+    int window = 1;                          // steps of one env speculated together (1 = the serial-in-time kernel)
     // staging for shipsim_step_host (allocated on first use, sized for the largest K seen)
     int32_t *d_act = nullptr; float *d_obs = nullptr; float *d_rew = nullptr; uint8_t *d_done = nullptr;
     int stage_K = 0;
     cudaStream_t copy_stream = nullptr;      // shipsim_step_host: results of chunk i go home while chunk i+1 is computed
     cudaEvent_t chunk_done[2] = {nullptr, nullptr};
     int64_t launches = 0;
-    LaunchShape shape{1, kThreads, 0};
+    LaunchShape shape{1, kThreads, 0, 1};
 };
 
 static thread_local std::string g_err;
@@ -79,6 +80,8 @@ extern "C" int shipsim_config_default(shipsim_config *c)
     c->mass = 5.f; c->thrust = 100.f;                         // models.py:87,107
     c->goal_radius = 5.f; c->step_penalty = -0.01f; c->spawn_y = 25.f;   // game.py:82, ship_env.py:13, game.py:274
     c->lanes_per_env = 0;
+    c->steps_in_flight = 0;
+    c->reserved0 = 0;
     return SHIPSIM_OK;
 }
 
@@ -184,6 +187,9 @@ extern "C" int shipsim_create(const shipsim_config *cfg, int device, shipsim_t *
         const int g = cfg->lanes_per_env;
         if (g != 0 && g != 1 && g != 2 && g != 4 && g != 8 && g != 16 && g != 32)
             return fail(SHIPSIM_ERR_ARG, "lanes_per_env must be 0 (auto), 1, 2, 4, 8, 16 or 32");
+        const int w = cfg->steps_in_flight;
+        if (w != 0 && w != 1 && w != 4 && w != 8 && w != 16 && w != 32)
+            return fail(SHIPSIM_ERR_ARG, "steps_in_flight must be 0 (auto), 1 (off), 4, 8, 16 or 32");
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(SHIPSIM_ERR_CUDA, "no CUDA device: libshipsim has no CPU fallback");
@@ -205,6 +211,14 @@ extern "C" int shipsim_create(const shipsim_config *cfg, int device, shipsim_t *
         const int n = cfg->num_envs;
         const int g = n < 8192 ? 8 : (n < 24576 ? 4 : (n < 49152 ? 2 : 1));
         h->lanes = g;
+    }
+    if (cfg->steps_in_flight) {
+        h->window = cfg->steps_in_flight;
+    } else {
+        // Auto: batches too small to fill the machine are bound by the latency of one dependent step after another;
+        // the window kernel speculates several steps of an env at once (shipsim_window.cu).  Explicit lanes_per_env
+        // asks for the serial-in-time kernel.
+        h->window = (!cfg->lanes_per_env && cfg->num_envs <= SHIPSIM_WINDOW_AUTO_MAX_ENVS) ? 8 : 1;
     }
     *out = h;
     return SHIPSIM_OK;
@@ -442,7 +456,9 @@ extern "C" int shipsim_step(shipsim_t *h, const void *dev_actions, int action_dt
     StepParams p = h->p;
     p.actions = dev_actions; p.action_dtype = action_dtype; p.K = K;
     p.obs = (float4 *)dev_obs; p.reward = dev_reward; p.done = dev_done;
-    CU(launch_step(p, h->lanes, (cudaStream_t)stream, &h->shape));
+    // the window kernel needs the actions of the whole rollout up front and at least one full window of steps
+    if (h->window > 1 && K >= h->window) CU(launch_window(p, h->window, (cudaStream_t)stream, &h->shape));
+    else CU(launch_step(p, h->lanes, (cudaStream_t)stream, &h->shape));
     h->p.step0 += (unsigned)K;
     h->launches++;
     return SHIPSIM_OK;
@@ -576,5 +592,12 @@ extern "C" int shipsim_launch_shape(const shipsim_t *h, int32_t *lanes, int32_t 
     if (lanes) *lanes = h->shape.lanes_per_env;
     if (threads) *threads = h->shape.threads;
     if (ctas) *ctas = h->shape.blocks;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_launch_window(const shipsim_t *h, int32_t *steps_in_flight)
+{
+    if (!h || !steps_in_flight) return fail(SHIPSIM_ERR_ARG, "NULL argument");
+    *steps_in_flight = h->shape.window;
     return SHIPSIM_OK;
 }

@@ -11,7 +11,7 @@
 //   * SAT pass (whole warp, rare): 32/lps envs at a time, one lane per (env, bank edge).
 // The loop is rotated: an iteration starts with the pose already integrated, so that the grid cell of the pose an
 // iteration works on was requested a whole iteration earlier.
-#include "shipsim_device.cuh"
+#include "shipsim_geom.cuh"
 #include "shipsim_launch.h"
 
 #ifndef SHIPSIM_MIN_BLOCKS
@@ -19,199 +19,6 @@
 #endif
 
 namespace shipsim {
-
-// actions[k][e]: `ap` walks down this env's column (stride = one row of the action tensor, in bytes)
-__device__ __forceinline__ int load_action(const StepParams &p, const char *ap, int k, long long gid)
-{
-    switch (p.action_dtype) {
-        case 0: return __ldg(reinterpret_cast<const int *>(ap));
-        case 1: return (int)__ldg(reinterpret_cast<const long long *>(ap));
-        case 2: return (int)__ldg(reinterpret_cast<const unsigned char *>(ap));
-        default: return random_action(p, gid, p.step0 + (unsigned)k);
-    }
-}
-
-// One bank-normal axis of the separating-axis test: does plane `ed` of the bank have the whole ship (rotated hull
-// rx/ry about the body origin bx/by) strictly in front of it?
-__device__ __forceinline__ bool bank_axis_separates(const float4 ed, const float (&rx)[kShipVerts], const float (&ry)[kShipVerts],
-                                                    float bx, float by)
-{
-    float m = fmaf(ed.x, rx[0], __fmul_rn(ed.y, ry[0]));
-#pragma unroll
-    for (int j = 1; j < kShipVerts; ++j) m = fminf(m, fmaf(ed.x, rx[j], __fmul_rn(ed.y, ry[j])));
-    const float base = fmaf(ed.x, bx - ed.z, __fmul_rn(ed.y, by - ed.w));
-    return base + m > 0.f;
-}
-
-// half extents of the rotated hull's AABB (cpPolyShapeCacheData): the lidar origin is the body origin plus these
-// (models.py:51-53).  Hull vertex 0 is the body origin.
-__device__ __forceinline__ void hull_half_extents(const StepParams &p, float c, float s, float &hx, float &hy)
-{
-    float minx = 0.f, maxx = 0.f, miny = 0.f, maxy = 0.f;
-#pragma unroll
-    for (int j = 1; j < kShipVerts; ++j) {
-        const float wx = p.ship_lx[j] * c - p.ship_ly[j] * s;
-        const float wy = p.ship_lx[j] * s + p.ship_ly[j] * c;
-        minx = fminf(minx, wx); maxx = fmaxf(maxx, wx); miny = fminf(miny, wy); maxy = fmaxf(maxy, wy);
-    }
-    hx = 0.5f * (maxx - minx);
-    hy = 0.5f * (maxy - miny);
-}
-
-// Reach-grid cell of the lidar origin (ox, oy): which bank edges a ray starting there can touch at all.
-__device__ __forceinline__ uint4 load_cell(const StepParams &p, int scen, float ox, float oy)
-{
-    int ix = __float2int_rd((ox - p.gridp.x0) * p.gridp.inv_cx);
-    int iy = __float2int_rd((oy - p.gridp.y0) * p.gridp.inv_cy);
-    ix = min(max(ix, 0), kGridN - 1);
-    iy = min(max(iy, 0), kGridN - 1);
-    return __ldg(p.grid + ((size_t)scen * kGridN + iy) * kGridN + ix);
-}
-
-// A candidate plane seen from the ray origin (ox, oy) = (x + hx, y + hy), evaluated in double from the plane the
-// reference's cpSplittingPlane holds: d = n.(o - v_i), ta = cross(n, o - v_i).
-struct PlaneEval { float d, ta, nx, ny, len; };
-
-__device__ __forceinline__ PlaneEval eval_plane_rec(const double2 nd, const float4 ev, double xd, double yd, double hxd, double hyd)
-{
-    const double qx = (xd - (double)ev.x) + hxd, qy = (yd - (double)ev.y) + hyd;     // origin - v_i
-    PlaneEval o;
-    o.d = (float)(nd.x * qx + nd.y * qy);
-    o.ta = (float)(nd.x * qy - nd.y * qx);
-    o.nx = (float)nd.x;
-    o.ny = (float)nd.y;
-    o.len = ev.z;
-    return o;
-}
-
-__device__ __forceinline__ PlaneEval eval_plane(const EdgeD *E, double xd, double yd, double hxd, double hyd)
-{
-    return eval_plane_rec(__ldg(reinterpret_cast<const double2 *>(E)), __ldg(reinterpret_cast<const float4 *>(E) + 1), xd, yd, hxd, hyd);
-}
-
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-// One ray (direction dir, length L) against one candidate plane: cpPolyShapeSegmentQuery's loop body.  nxl / nyl =
-// -L * n.  The reference computes t = d / max(an - bn, DBL_MIN) and rejects t outside [0, 1]: with d >= 0 that is
-// an - bn > 0 and d <= an - bn (d == 0 with the ray leaving the plane can only yield the origin itself, which the
-// edge-extent test or the inside test has already decided).  `val` = |hit - origin|.
-__device__ __forceinline__ bool ray_vs_plane(float d, float ta, float nxl, float nyl, float len, float dirx, float diry, float L, float &val)
-{
-    const float denom = nxl * dirx + nyl * diry;                          // an - bn
-    const float cr = nxl * diry - nyl * dirx;                             // -L * cross(n, dir)
-    const float t = d * rcp_approx(denom);
-    const float tang = ta - t * cr;                                       // cross(n, hit - v_i)
-    val = t * L;
-    return d >= 0.f && denom > 0.f && d <= denom && tang >= -len && tang <= 0.f;
-}
-
-constexpr int kMaxCand = 4;                  // candidate planes a scratch row holds (more -> serial path)
-constexpr int kScr4 = 1 + 2 * kMaxCand;      // scratch row: header + two float4 per plane (odd stride: conflict-free)
-// header.z bits
-constexpr int kHdrIn0 = 1 << 8, kHdrIn1 = 1 << 9, kHdrBig = 1 << 10;
-
-// Plane phase for one env at pose (x, y, c, s): fills the env's scratch row for the next lidar query and returns,
-// when WITH_SAT, bit b set <=> bank b is near and none of its candidate planes has the whole ship in front of it
-// (=> the full separating-axis pass has to decide).  Scratch row:
-//   [0]      c, s, bits(n | in0<<8 | in1<<9 | big<<10), 0
-//   [1+2i]   d, ta, -L*nx, -L*ny        [2+2i]  len, bank (0.f / 1.f), 0, 0
-//   big row (more than kMaxCand candidates; rays are then cast serially by the owner lane):
-//   [1]      x, y, hx, hy               [2]     bits(scen), bits(m0), bits(m1), bits(flags)
-// STAGED: the raw EdgeD record of candidate i has already been copied (cp.async) into raw[2i], raw[2i+1]; the
-// record carries its own index (bank * kMaxHull + edge) in `pad`, so the candidate masks need not be walked again.
-template <bool WITH_SAT, bool STAGED>
-__device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, float y, float hx, float hy, float c, float s, int scen,
-                                                const uint4 cell, float4 *row, const float4 *raw = nullptr)
-{
-    unsigned m0 = cell.x, m1 = cell.y;
-    const unsigned near = ((m0 != 0u || (cell.z & 1u)) ? 1u : 0u) | ((m1 != 0u || (cell.z & 2u)) ? 2u : 0u);
-    const int ncand = (int)((cell.z >> 8) & 0xffu);
-    if (ncand > kMaxCand) {
-        row[0] = make_float4(c, s, __int_as_float(kHdrBig), 0.f);
-        row[1] = make_float4(x, y, hx, hy);
-        row[2] = make_float4(__int_as_float(scen), __uint_as_float(m0), __uint_as_float(m1), __uint_as_float(cell.z));
-        return near;
-    }
-    const float L = p.lidar_len;
-    const EdgeD *E = p.edges_d + (size_t)scen * (2 * kMaxHull);
-    const double xd = (double)x, yd = (double)y, hxd = (double)hx, hyd = (double)hy;
-    unsigned outm = 0u, sepm = 0u;
-#pragma unroll 1
-    for (int n = 0; n < ncand; ++n) {
-        double2 nd;
-        float4 ev;
-        if (STAGED) {
-            nd = *reinterpret_cast<const double2 *>(raw + 2 * n);
-            ev = raw[2 * n + 1];
-        } else {
-            int idx;
-            if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
-            nd = __ldg(reinterpret_cast<const double2 *>(E + idx));
-            ev = __ldg(reinterpret_cast<const float4 *>(E + idx) + 1);
-        }
-        const bool bank1 = __float_as_int(ev.w) >= kMaxHull;
-        const unsigned bbit = bank1 ? 2u : 1u;
-        const PlaneEval pe = eval_plane_rec(nd, ev, xd, yd, hxd, hyd);
-        if (pe.d > 0.f) outm |= bbit;
-        if (WITH_SAT) {
-            // does this bank plane have the whole ship in front of it?  n.(hull vertex j - v_i) = d - n.h + (R^T n).l_j:
-            // the normal is rotated into the body frame, where the hull is constant (vertex 0 is the body origin)
-            const float bnx = pe.nx * c + pe.ny * s, bny = pe.ny * c - pe.nx * s;
-            float m = 0.f;
-#pragma unroll
-            for (int j = 1; j < kShipVerts; ++j) m = fminf(m, bnx * p.ship_lx[j] + bny * p.ship_ly[j]);
-            if (pe.d - (pe.nx * hx + pe.ny * hy) + m > 0.f) sepm |= bbit;
-        }
-        row[1 + 2 * n] = make_float4(pe.d, pe.ta, -L * pe.nx, -L * pe.ny);
-        row[2 + 2 * n] = make_float4(pe.len, bank1 ? 1.f : 0.f, 0.f, 0.f);
-    }
-    // cpShapeSegmentQuery: start point inside the shape => alpha = 0 and `point` stays at the ray end
-    const unsigned inm = cell.z & 3u & ~outm;
-    row[0] = make_float4(c, s, __int_as_float(ncand | (int)(inm << 8)), 0.f);
-    return near & ~sepm;
-}
-
-// Serial LiDAR.query of one env by one lane: only for cells with more than kMaxCand candidate planes.
-__device__ __noinline__ void ray_query_serial(const StepParams &p, const float4 *row, float *lid)
-{
-    const float L = p.lidar_len;
-    const float4 h = row[0], a = row[1], b4 = row[2];
-    const float c = h.x, s = h.y;
-    const int scen = __float_as_int(b4.x);
-    const unsigned masks[2] = {__float_as_uint(b4.y), __float_as_uint(b4.z)};
-    const unsigned flags = __float_as_uint(b4.w);
-    const EdgeD *E = p.edges_d + (size_t)scen * (2 * kMaxHull);
-    const double xd = (double)a.x, yd = (double)a.y, hxd = (double)a.z, hyd = (double)a.w;
-    unsigned pend = (1u << kBeams) - 1u;
-    for (int b = 0; b < 2; ++b) {
-        bool out = false;
-        unsigned hitm = 0u;
-        float v[kBeams];
-        for (unsigned m = masks[b]; m; m &= m - 1u) {
-            const PlaneEval pe = eval_plane(E + b * kMaxHull + (__ffs(m) - 1), xd, yd, hxd, hyd);
-            out = out || (pe.d > 0.f);
-#pragma unroll
-            for (int j = 0; j < kBeams; ++j) {
-                const float dirx = c * p.ray_c[j] - s * p.ray_s[j], diry = s * p.ray_c[j] + c * p.ray_s[j];
-                float val;
-                if (ray_vs_plane(pe.d, pe.ta, -L * pe.nx, -L * pe.ny, pe.len, dirx, diry, L, val)) { v[j] = val; hitm |= 1u << j; }
-            }
-        }
-        const bool inside = ((flags >> b) & 1u) && !out;
-#pragma unroll
-        for (int j = 0; j < kBeams; ++j)
-            if ((pend >> j) & 1u) {
-                if (inside) lid[j] = L;
-                else if ((hitm >> j) & 1u) lid[j] = v[j];
-            }
-        pend &= inside ? 0u : ~hitm;
-    }
-}
 
 // MINB = CTAs per SM the register allocation aims for: 5 (96 registers) pays off only when the grid is large enough
 // to fill them, otherwise 4 (128 registers, less rematerialisation).
@@ -801,7 +608,7 @@ static cudaError_t launch_g(const StepParams &p, cudaStream_t stream, LaunchShap
 {
     const int envs_per_cta = kThreads / G;
     const int blocks = (p.N + envs_per_cta - 1) / envs_per_cta;
-    if (shape) { shape->lanes_per_env = G; shape->threads = kThreads; shape->blocks = blocks; }
+    if (shape) { shape->lanes_per_env = G; shape->threads = kThreads; shape->blocks = blocks; shape->window = 1; }
     bool launched = false;
     if constexpr (G == 1) {
         if (blocks >= 148 * 8) {

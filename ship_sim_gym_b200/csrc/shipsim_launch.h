@@ -9,9 +9,11 @@ struct StepParams;
 struct EdgeD;
 constexpr int kThreads = 128;
 
-struct LaunchShape { int lanes_per_env, threads, blocks; };
+struct LaunchShape { int lanes_per_env, threads, blocks, window; };
 
 cudaError_t launch_step(const StepParams &p, int lanes_per_env, cudaStream_t stream, LaunchShape *shape);
+// time-parallel variant (shipsim_window.cu): `window` = 4, 8, 16 or 32 speculated steps per env
+cudaError_t launch_window(const StepParams &p, int window, cudaStream_t stream, LaunchShape *shape);
 cudaError_t launch_reset(const StepParams &p, const uint8_t *mask, const int *scenario, int first, float4 *obs,
                          cudaStream_t stream);
 cudaError_t launch_build_grid(const double *hull_xy, const int *hull_n, int n_scen, int maxv_in, double gx0, double gy0,

@@ -1,0 +1,539 @@
+// shipsim_window.cu -- time-parallel ("window") variant of the fused ShipEnv step kernel, for latency-bound batches.
+// sm_100a only.  Same transition as step_kernel (shipsim_kernels.cu), same helper functions
+// (shipsim_geom.cuh), bit-identical results (tests/test_gpu_window.py).
+//
+// Why.  With few envs per SM (4,096 envs = 28 per SM) a K-step rollout is a chain of K dependent iterations and the
+// machine idles on instruction latency.  But only the cheap part of a step is sequential: the rigid-body recurrence
+// (cpBodyUpdatePosition / cpBodyUpdateVelocity: ~10 flops) and the rudder clamp.  Everything expensive -- the lidar
+// query, the ship-vs-bank overlap test, the goal tests, the observation frame -- is a pure function of one pose and
+// feeds back into the trajectory only through `done` (auto-reset).  So, when the actions of the rollout are known up
+// front (they are: shipsim_step takes the whole [K][N] action tensor), T consecutive steps of one env are SPECULATED:
+//   1. every lane of the env's group runs the T-step physics recurrence (redundantly, in lockstep, no traffic) and
+//      keeps the pose of "its" step t = lane % T;
+//   2. lane t does the pose-dependent work of step t -- reach-grid lookup, plane phase, goal tests, out-of-bounds --
+//      and the cooperative ray / separating-axis passes run over (env, step) pairs instead of envs;
+//   3. the sequential leftovers are resolved with short scans: goals taken (prefix OR), episode return (ordered sum,
+//      same rounding as the serial kernel), sticky lidar readings (models.py:71: a miss keeps the last hit);
+//   4. the window is cut after the first `done`: steps beyond it are discarded, the env resets and the next window
+//      starts from the reset state (episodes last ~50 steps, so a window of 8 wastes ~7 % of its lanes).
+// A warp holds E = 32/T envs; envs of a warp advance independently (each has its own step cursor k0).
+//
+// Shared-memory rings (per env, T+1 slots): observation frames and plane-phase rows.  Slot cb is the "carry": the
+// frame / planes of the last committed step (or of the reset), i.e. what step k0 starts from; slot cb+1+t belongs to
+// speculated step t.  Committing n steps just advances cb by n.
+#include "shipsim_geom.cuh"
+#include "shipsim_launch.h"
+
+namespace shipsim {
+
+template <int T, int HIST>
+__global__ void __launch_bounds__(kThreads, 4) window_kernel(const __grid_constant__ StepParams p)
+{
+    constexpr int E = 32 / T;                   // envs per warp
+    constexpr int NW = kThreads / 32;
+    constexpr int OBS4 = 4 * HIST;              // float4 per obs row
+    constexpr int NS = T + 1;                   // ring slots per env
+    constexpr int FS4 = 5;                      // float4 per frame slot (4 used; odd stride: conflict-free)
+    constexpr int FR4 = NS * FS4;               // float4 per env frame ring
+    constexpr int SC4 = NS * kScr4;             // float4 per env plane-row ring
+    constexpr float kMiss = -2.f;               // "this ray did not hit at this step" until the sticky scan resolves it
+    __shared__ float4 s_frame[NW * E * FR4];
+    __shared__ float4 s_scr[NW * E * SC4];
+    __shared__ float2 s_goal[NW * E * kGoals];
+    __shared__ float4 s_rf[NW * E * 2];         // reset frame, first two float4 (the rest is -1)
+    __shared__ float4 s_ph[NW * 32 * 2];        // physics scan -> lanes: (th, w, bits(rudder), -) and (x, y, vx, vy) per step
+    __shared__ float s_ray[2 * 32];
+    __shared__ unsigned s_src[NW][32];          // ray pass: compacted (plane row | frame offset) of the needy steps
+    __shared__ float s_stat[NW][8];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int el = lane / T, t = lane % T;
+    const int gbase = el * T;                   // first lane of this env's group
+    const unsigned segmask = T == 32 ? kFull : (((1u << T) - 1u) << gbase);
+    const int warp_env0 = (blockIdx.x * NW + warp) * E;
+    const int e = warp_env0 + el;
+    const bool valid = e < p.N;
+    const int ec = valid ? e : p.N - 1;         // lanes of idle groups shadow the last env; they never store
+    const int wfr0 = warp * E * FR4, wsc0 = warp * E * SC4;
+    const int fr0 = wfr0 + el * FR4, sc0 = wsc0 + el * SC4;
+    const int goal0 = (warp * E + el) * kGoals;
+    const int rf0 = (warp * E + el) * 2;
+    const float L = p.lidar_len;
+    const long long gid = p.env_id_offset + e;
+#define stat (s_stat[warp])
+    auto ring = [](int s) { return s >= NS ? s - NS : s; };
+
+    // lane roles in the cooperative passes (as in step_kernel)
+    const int rslot = lane / kBeams;
+    const int rj = lane - rslot * kBeams;
+    if (threadIdx.x < 32) {
+        s_ray[threadIdx.x] = p.ray_c[threadIdx.x % kBeams];
+        s_ray[32 + threadIdx.x] = p.ray_s[threadIdx.x % kBeams];
+    }
+    if (lane < 8) stat[lane] = 0.f;
+    const int lps_sh = p.hull_max <= 8 ? 3 : (p.hull_max <= 16 ? 4 : 5);
+    const int lps = 1 << lps_sh, nslots = 32 >> lps_sh;
+    const int sslot = lane >> lps_sh, sel = lane & (lps - 1);
+    const unsigned slotmask = lps == 32 ? kFull : (((1u << lps) - 1u) << (sslot * lps));
+
+    const size_t act_esize = p.action_dtype == 1 ? 8 : (p.action_dtype == 2 ? 1 : 4);
+    const char *act0 = reinterpret_cast<const char *>(p.actions) + (size_t)ec * act_esize;
+    const size_t act_stride = (size_t)p.N * act_esize;
+
+    EnvRegs r;
+    int cb = 0;                                 // ring slot of the carry
+    int k0 = 0;                                 // this env's next step
+    bool goals_dirty = false;
+    float c0, s0;                               // trig of the pose step k0 starts from
+    {
+        float4 l0, l1, l2, g0, g1, g2;
+        load_env(p, ec, r, l0, l1, l2, g0, g1, g2);
+        float2 g[kGoals];
+        unpack_goals(g0, g1, g2, g);
+        float gx, gy;
+        closest_goal(g, r.alive, r.x, r.y, gx, gy);
+        sincos_fast(r.th, s0, c0);
+        if (t == 0) {
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i) s_goal[goal0 + i] = g[i];
+            float4 *f = s_frame + fr0;          // carry frame = frame of the current state
+            f[0] = make_float4(r.x, r.y, (float)r.rudder, r.th);
+            f[1] = make_float4(gx, gy, l0.x, l0.y);
+            f[2] = make_float4(l0.z, l0.w, l1.x, l1.y);
+            f[3] = make_float4(l1.z, l1.w, l2.x, l2.y);
+            float hx, hy;                       // carry row = planes of the current pose
+            hull_half_extents(p, c0, s0, hx, hy);
+            const uint4 cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
+            float4 *row = s_scr + sc0;
+            if ((cell.x | cell.y | (cell.z & 3u)) != 0u) plane_phase<false, false>(p, r.x, r.y, hx, hy, c0, s0, r.scen, cell, row);
+            else row[0] = make_float4(c0, s0, 0.f, 0.f);
+        }
+    }
+    int a_my = 3;
+    if (valid && t < p.K) a_my = load_action(p, act0 + (size_t)t * act_stride, t, gid);
+    __syncthreads();
+
+#pragma unroll 1
+    while (true) {
+        const int nvalid = valid ? min(T, p.K - k0) : 0;        // steps this env still has, capped by the window
+        if (__ballot_sync(kFull, nvalid > 0) == 0u) break;
+        const bool active = t < nvalid;
+
+        // ---- 1. the sequential part, T steps: handle_discrete_action (game.py:140-153), cpBodyUpdatePosition,
+        // cpBodyUpdateVelocity -- the same operations in the same order as step_kernel, split so that as little as
+        // possible is serial.  Every lane of the group runs the scans in lockstep (no divergence, no waiting); the
+        // group's first lane drops each step's result into shared memory and lane t picks up step t.
+        float mx, my, mth, mvx, mvy, mw, mc, ms;
+        int mrud;
+        {
+            float4 *ph = s_ph + (warp * 32 + gbase) * 2;
+            // scan 1: rudder, angular velocity, angle (these do not depend on the trig of the pose)
+            {
+                float th = r.th, w = r.w;
+                int rud = r.rudder;
+#pragma unroll 4
+                for (int i = 0; i < T; ++i) {
+                    const int a = __shfl_sync(kFull, a_my, gbase + i);
+                    const float dw = a == 0 ? -p.ang_dt * (float)rud : 0.f;
+                    rud = a == 1 ? max(rud - 5, -10) : (a == 2 ? min(rud + 5, 10) : rud);
+                    th += w * p.dt;
+                    w = w * p.damping + dw;
+                    if (t == 0) ph[2 * i] = make_float4(th, w, __int_as_float(rud), 0.f);
+                }
+            }
+            __syncwarp();
+            {
+                const float4 v = ph[2 * t];
+                mth = v.x; mw = v.y; mrud = __float_as_int(v.z);
+            }
+            sincos_fast(mth, ms, mc);                   // one sincos per lane instead of T per lane
+            // thrust of step t acts along the heading the step STARTS from: the trig of step t-1 (or of the carry)
+            float pc = __shfl_up_sync(kFull, mc, 1, T), ps = __shfl_up_sync(kFull, ms, 1, T);
+            if (t == 0) { pc = c0; ps = s0; }
+            float dvx_t = 0.f, dvy_t = 0.f;
+            if (a_my == 0) { dvx_t = -p.acc_dt * ps; dvy_t = p.acc_dt * pc; }
+            // scan 2: velocity and position
+            {
+                float x = r.x, y = r.y, vx = r.vx, vy = r.vy;
+#pragma unroll 4
+                for (int i = 0; i < T; ++i) {
+                    const float dvx = __shfl_sync(kFull, dvx_t, gbase + i), dvy = __shfl_sync(kFull, dvy_t, gbase + i);
+                    x += vx * p.dt;
+                    y += vy * p.dt;
+                    vx = vx * p.damping + dvx;
+                    vy = vy * p.damping + dvy;
+                    if (t == 0) ph[2 * i + 1] = make_float4(x, y, vx, vy);
+                }
+            }
+            __syncwarp();
+            {
+                const float4 v = ph[2 * t + 1];
+                mx = v.x; my = v.y; mvx = v.z; mvy = v.w;
+            }
+        }
+
+        // ---- 2. pose-dependent work of step t at (mx, my, mth): reach-grid cell, candidate planes staged by cp.async
+        const int myslot_ring = ring(cb + 1 + t);
+        float4 *myrow = s_scr + sc0 + myslot_ring * kScr4;
+        float4 *myfr = s_frame + fr0 + myslot_ring * FS4;
+        float hx = 0.f, hy = 0.f;
+        uint4 cell = make_uint4(0u, 0u, 0u, 0xffffffffu);
+        if (active) {
+            hull_half_extents(p, mc, ms, hx, hy);
+            cell = load_cell(p, r.scen, mx + hx, my + hy);
+        }
+
+        // goals (collide_goal, game.py:243-257): which goals does the hull touch at this pose?  (whether they are
+        // still alive is settled by the scan below)
+        float2 g[kGoals];
+        float gd2[kGoals];
+        unsigned touch = 0u;
+        {
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i) {
+                g[i] = s_goal[goal0 + i];
+                const float ux = g[i].x - mx, uy = g[i].y - my;
+                gd2[i] = ux * ux + uy * uy;
+            }
+            unsigned cand = 0u;
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i)
+                if (active && ((r.alive >> i) & 1) && gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
+            while (cand) {
+                const int i = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                float ux = g[0].x, uy = g[0].y;
+#pragma unroll
+                for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
+                ux -= mx; uy -= my;
+                const float qx = ux * mc + uy * ms, qy = -ux * ms + uy * mc;
+                if (!goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy)) touch |= 1u << i;
+            }
+        }
+        // this step's lidar slots: "no hit" until the ray pass says otherwise
+        reinterpret_cast<float2 *>(myfr + 1)[1] = make_float2(kMiss, kMiss);
+        myfr[2] = make_float4(kMiss, kMiss, kMiss, kMiss);
+        myfr[3] = make_float4(kMiss, kMiss, kMiss, kMiss);
+
+        const bool near_any = active && (cell.x | cell.y | (cell.z & 3u)) != 0u;
+        const bool staged = near_any && ((cell.z >> 8) & 0xffu) <= (unsigned)kMaxCand;
+        if (staged) {
+            const float4 *E4 = reinterpret_cast<const float4 *>(p.edges_d + (size_t)r.scen * (2 * kMaxHull));
+#pragma unroll
+            for (int n = 0; n < kMaxCand; ++n) {
+                const unsigned idx = (cell.w >> (8 * n)) & 0xffu;
+                if (idx != 0xffu) {
+                    cp_async16(myrow + 1 + 2 * n, E4 + 2 * idx);
+                    cp_async16(myrow + 2 + 2 * n, E4 + 2 * idx + 1);
+                }
+            }
+        }
+        const bool oob = (mx < 0.f) || (mx > p.W) || (my < 0.f) || (my > p.H);
+
+        // ---- plane phase at pose t: lidar planes of step t+1 + ship-vs-bank pre-test of step t
+        cp_async_wait_all();
+        unsigned ask = 0u;
+        if (staged) ask = plane_phase<true, true>(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow, myrow + 1);
+        else if (near_any) ask = plane_phase<true, false>(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow);
+        else if (active) myrow[0] = make_float4(mc, ms, 0.f, 0.f);
+        __syncwarp();
+
+        // ---- overlap test at the new pose -> collide_ship (game.py:232-241): separating-axis pass for the steps the
+        // plane phase could not settle (one lane per bank edge, 32/lps steps at a time)
+        bool colliding = false;
+        {
+            unsigned needs = __ballot_sync(kFull, ask != 0u);
+            while (needs) {
+                int src = -1, myslot = -1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (q < nslots && needs) {
+                        const int tt = __ffs(needs) - 1;
+                        needs &= needs - 1u;
+                        if (sslot == q) src = tt;
+                        if (tt == lane) myslot = q;
+                    }
+                }
+                const bool act_env = src >= 0;
+                const int srcl = act_env ? src : lane;
+                const float bx = __shfl_sync(kFull, mx, srcl), by = __shfl_sync(kFull, my, srcl);
+                const float bc = __shfl_sync(kFull, mc, srcl), bs = __shfl_sync(kFull, ms, srcl);
+                const unsigned bsa = __shfl_sync(kFull, (unsigned)r.scen | (ask << 28), srcl);
+                const float4 *rec = p.bank + (size_t)(bsa & 0x0fffffffu) * p.scen_stride4;
+                const float4 hdr = __ldg(rec + 4);
+                const float4 *bE = rec + kBankHeader4;
+                float rx[kShipVerts], ry[kShipVerts];
+#pragma unroll
+                for (int j = 0; j < kShipVerts; ++j) {
+                    rx[j] = p.ship_lx[j] * bc - p.ship_ly[j] * bs;
+                    ry[j] = p.ship_lx[j] * bs + p.ship_ly[j] * bc;
+                }
+                bool coll = false;
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    const bool do_b = act_env && ((bsa >> (28 + b)) & 1u) && !coll;
+                    const int nb = __float_as_int(b ? hdr.w : hdr.z);
+                    const bool actl = do_b && sel < nb;
+                    float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (actl) ed = __ldg(bE + b * p.maxv + sel);
+                    const unsigned sb = __ballot_sync(kFull, actl && bank_axis_separates(ed, rx, ry, bx, by));
+                    bool sep = (sb & slotmask) != 0u;
+                    if (__ballot_sync(kFull, do_b && !sep)) {
+#pragma unroll
+                        for (int j = 0; j < kShipVerts; ++j) {
+                            const float nx = p.ship_nx[j] * bc - p.ship_ny[j] * bs;
+                            const float ny = p.ship_nx[j] * bs + p.ship_ny[j] * bc;
+                            const float pr = actl ? nx * (ed.z - bx) + ny * (ed.w - by) : 3.0e38f;
+                            const int mn = __reduce_min_sync(slotmask, f2ord(pr));
+                            sep = sep || (mn > f2ord(p.ship_off[j]));
+                        }
+                    }
+                    if (do_b && !sep) coll = true;
+                }
+                const unsigned res = __ballot_sync(kFull, coll);
+                if (myslot >= 0 && ((res >> (myslot * lps)) & 1u)) colliding = true;
+            }
+        }
+
+        // ---- LiDAR.query (models.py:39-76) of step t at its PRE-integration pose = the pose of step t-1 (ring slot
+        // cb + t; the carry for t = 0).  Up to three needy steps per pass, lanes 0-9 / 10-19 / 20-29 = their rays.
+        {
+            const int srcrow = sc0 + ring(cb + t) * kScr4;
+            const int hz_own = active ? __float_as_int(s_scr[srcrow].z) : 0;
+            const bool big = (hz_own & kHdrBig) != 0;
+            const bool wants = (hz_own & 0x3ff) != 0;
+            const unsigned need = __ballot_sync(kFull, wants);
+            if (big) ray_query_serial(p, s_scr + srcrow, reinterpret_cast<float *>(myfr) + 6);
+            if (need) {
+                if (wants) s_src[warp][__popc(need & ((1u << lane) - 1u))] =
+                    (unsigned)(srcrow - wsc0) | ((unsigned)((fr0 - wfr0 + myslot_ring * FS4) * 4 + 6) << 16);
+                __syncwarp();
+                const int cnt = __popc(need);
+                const float ray_c = s_ray[lane], ray_s = s_ray[32 + lane];
+#pragma unroll 1
+                for (int q = rslot; q < cnt; q += 3) {
+                    if (rslot < 3) {
+                        const unsigned sw = s_src[warp][q];
+                        const int rw = wsc0 + (int)(sw & 0xffffu);
+                        const float4 hdr = s_scr[rw];
+                        const float dirx = hdr.x * ray_c - hdr.y * ray_s, diry = hdr.y * ray_c + hdr.x * ray_s;
+                        const int hz = __float_as_int(hdr.z);
+                        const int n = hz & 0xff;
+                        float v0 = -1.f, v1 = -1.f;
+#pragma unroll 1
+                        for (int i = 0; i < n; ++i) {
+                            const float4 e0 = s_scr[rw + 1 + 2 * i];
+                            const float2 e1 = *reinterpret_cast<const float2 *>(s_scr + rw + 2 + 2 * i);
+                            float val;
+                            const bool ok = ray_vs_plane(e0.x, e0.y, e0.z, e0.w, e1.x, dirx, diry, L, val);
+                            if (ok && e1.y == 0.f) v0 = val;
+                            if (ok && e1.y != 0.f) v1 = val;
+                        }
+                        if (hz & kHdrIn0) v0 = L;
+                        if (hz & kHdrIn1) v1 = L;
+                        const float v = v0 >= 0.f ? v0 : v1;
+                        if (v >= 0.f) reinterpret_cast<float *>(s_frame + wfr0)[(sw >> 16) + rj] = v;
+                    }
+                }
+            }
+        }
+
+        // ---- 3. the sequential leftovers.  Goals taken so far in the window: prefix OR of the touch masks.
+        unsigned inc = touch;
+#pragma unroll
+        for (int d = 1; d < T; d <<= 1) {
+            const unsigned o = __shfl_up_sync(kFull, inc, d, T);
+            if (t >= d) inc |= o;
+        }
+        unsigned exc = __shfl_up_sync(kFull, inc, 1, T);
+        if (t == 0) exc = 0u;
+        const int alive_prev = r.alive & ~(int)exc, alive_t = r.alive & ~(int)inc;
+        const bool goal_reached = (alive_prev & (int)touch) != 0;
+        const int steps_t = r.steps + t + 1;
+        // ShipEnv.determine_reward (ship_env.py:62-77) / is_done (ship_env.py:115-134)
+        const float reward = goal_reached ? 1.f : (oob ? -1.f : p.step_penalty);
+        const bool all_goals = alive_t == 0;
+        const bool timeout = steps_t >= p.max_steps;
+        const bool done = colliding || all_goals || oob || timeout;
+        // cut the window after the first done step (auto-reset): everything speculated beyond it is discarded
+        const unsigned dmask = __ballot_sync(kFull, active && done) & segmask;
+        const bool do_reset = p.auto_reset && dmask != 0u;
+        const int ncommit = do_reset ? __ffs(dmask) - gbase : nvalid;
+        const bool commit = t < ncommit;
+        // episode return: ordered sum, same rounding as one step at a time
+        float my_ret = 0.f;
+        {
+            float acc = r.ret;
+#pragma unroll 8
+            for (int i = 0; i < T; ++i) {
+                acc += __shfl_sync(kFull, reward, gbase + i);
+                if (i == t) my_ret = acc;
+            }
+        }
+        if (commit) {
+            if (goal_reached) atomicAdd(stat + 3, 1.f);
+            if (done) {
+                atomicAdd(stat + 0, 1.f); atomicAdd(stat + 1, my_ret); atomicAdd(stat + 2, (float)steps_t);
+                if (colliding) atomicAdd(stat + 4, 1.f);
+                if (oob) atomicAdd(stat + 5, 1.f);
+                if (timeout) atomicAdd(stat + 6, 1.f);
+                if (all_goals) atomicAdd(stat + 7, 1.f);
+            }
+        }
+        // this step's frame: pose, rudder, nearest remaining goal (closest_goal, game.py:333-349), and the lidar
+        // readings.  Sticky readings (models.py:71): a ray that missed keeps the reading of the last step at which it
+        // hit -- the latest hit at or before step t inside the window (found with a ballot per ray), else the carry's.
+        __syncwarp();                           // ray pass results are in the frame slots
+        {
+            float gx = -1.f, gy = -1.f, best = 3.0e38f;
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i)
+                if (((alive_t >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
+            float h[kBeams], cv[kBeams];
+            {
+                const float4 *cf = s_frame + fr0 + cb * FS4;
+                const float2 a0 = reinterpret_cast<const float2 *>(cf + 1)[1];
+                const float4 a1 = cf[2], a2 = cf[3];
+                cv[0] = a0.x; cv[1] = a0.y; cv[2] = a1.x; cv[3] = a1.y; cv[4] = a1.z; cv[5] = a1.w;
+                cv[6] = a2.x; cv[7] = a2.y; cv[8] = a2.z; cv[9] = a2.w;
+                const float2 b0 = reinterpret_cast<const float2 *>(myfr + 1)[1];
+                const float4 b1 = myfr[2], b2 = myfr[3];
+                h[0] = b0.x; h[1] = b0.y; h[2] = b1.x; h[3] = b1.y; h[4] = b1.z; h[5] = b1.w;
+                h[6] = b2.x; h[7] = b2.y; h[8] = b2.z; h[9] = b2.w;
+            }
+            const unsigned upto = segmask & ((2u << lane) - 1u);       // lanes of this env at steps <= t
+#pragma unroll
+            for (int j = 0; j < kBeams; ++j) {
+                const unsigned m = __ballot_sync(kFull, h[j] != kMiss) & upto;
+                const int src = m ? 31 - __clz(m) : lane;
+                const float v = __shfl_sync(kFull, h[j], src);
+                h[j] = m ? v : cv[j];
+            }
+            myfr[0] = make_float4(mx, my, (float)mrud, mth);
+            myfr[1] = make_float4(gx, gy, h[0], h[1]);
+            myfr[2] = make_float4(h[2], h[3], h[4], h[5]);
+            myfr[3] = make_float4(h[6], h[7], h[8], h[9]);
+        }
+
+        // ---- 4. the state the next window starts from: after the last committed step, or the reset
+        const int srcl = gbase + max(ncommit, 1) - 1;
+        EnvRegs rn;
+        rn.x = __shfl_sync(kFull, mx, srcl); rn.y = __shfl_sync(kFull, my, srcl); rn.th = __shfl_sync(kFull, mth, srcl);
+        rn.vx = __shfl_sync(kFull, mvx, srcl); rn.vy = __shfl_sync(kFull, mvy, srcl); rn.w = __shfl_sync(kFull, mw, srcl);
+        rn.ret = __shfl_sync(kFull, my_ret, srcl);
+        rn.rudder = __shfl_sync(kFull, mrud, srcl); rn.alive = __shfl_sync(kFull, alive_t, srcl);
+        rn.steps = r.steps + ncommit; rn.scen = r.scen; rn.episode = r.episode;
+        float c0n = __shfl_sync(kFull, mc, srcl), s0n = __shfl_sync(kFull, ms, srcl);
+        if (do_reset) {                                             // ShipEnv.reset (ship_env.py:171-184)
+            const int ep = r.episode + 1;
+            reset_env(p, rn, pick_scenario(p, gid, ep), ep);
+            c0n = 1.f; s0n = 0.f;
+            const float4 *rec = p.bank + (size_t)rn.scen * p.scen_stride4;
+            float2 gn[kGoals];
+            unpack_goals(__ldg(rec + 2), __ldg(rec + 3), __ldg(rec + 4), gn);
+            float rgx, rgy;
+            closest_goal(gn, rn.alive, rn.x, rn.y, rgx, rgy);
+            if (t == 0) {
+#pragma unroll
+                for (int i = 0; i < kGoals; ++i) s_goal[goal0 + i] = gn[i];
+                s_rf[rf0] = make_float4(rn.x, rn.y, 0.f, 0.f);
+                s_rf[rf0 + 1] = make_float4(rgx, rgy, -1.f, -1.f);
+            }
+            goals_dirty = true;
+        }
+        __syncwarp();
+
+        // ---- outputs of the committed steps.  Obs row of step t = [frame t-1 | frame t] = ring slots (cb+t, cb+t+1);
+        // OBS4 lanes per row, 32/OBS4 rows per round, 128-bit streaming stores.
+        if (p.obs) {
+            const float4 neg = make_float4(-1.f, -1.f, -1.f, -1.f);
+            const int col = lane % OBS4;
+            const int half = HIST == 2 ? (col >> 2) : 1, q = col & 3;
+#pragma unroll
+            for (int i = 0; i < OBS4; ++i) {
+                const int ridx = lane / OBS4 + i * (32 / OBS4);     // the row's owner lane
+                const int k0r = __shfl_sync(kFull, k0, ridx), ncr = __shfl_sync(kFull, ncommit, ridx);
+                const int cbr = __shfl_sync(kFull, cb, ridx);
+                const int rsr = __shfl_sync(kFull, (int)do_reset, ridx);
+                const int elr = ridx / T, tr = ridx % T;
+                if (tr < ncr) {
+                    float4 v;
+                    if (rsr && tr == ncr - 1)                       // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
+                        v = (half == 0 || q >= 2) ? neg : s_rf[(warp * E + elr) * 2 + q];
+                    else
+                        v = s_frame[wfr0 + elr * FR4 + ring(cbr + tr + half) * FS4 + q];
+                    __stcs(p.obs + ((size_t)(k0r + tr) * p.N + (warp_env0 + elr)) * OBS4 + col, v);
+                }
+            }
+        }
+        if (commit) {
+            const size_t row = (size_t)(k0 + t) * p.N + e;
+            if (p.reward) p.reward[row] = reward;
+            if (p.done) p.done[row] = done ? 1 : 0;
+        }
+        __syncwarp();                           // rows and frames have been read: the carry may move
+
+        if (ncommit > 0) {
+            const int ncb = ring(cb + ncommit);
+            if (do_reset) {                     // carry := reset frame + the spawn pose's planes (built at scenario upload)
+                if (t == 0) {
+                    float4 *f = s_frame + fr0 + ncb * FS4;
+                    const float4 neg = make_float4(-1.f, -1.f, -1.f, -1.f);
+                    f[0] = s_rf[rf0]; f[1] = s_rf[rf0 + 1]; f[2] = neg; f[3] = neg;
+                }
+                const float4 *sp = p.spawn_rows + (size_t)rn.scen * kScr4;
+                const float4 h0 = __ldg(sp);
+                const int hn = __float_as_int(h0.z);
+                const int nrow = (hn & kHdrBig) ? 2 : 2 * (hn & 0xff);
+                float4 *row = s_scr + sc0 + ncb * kScr4;
+                for (int i = t; i <= nrow; i += T) row[i] = i == 0 ? h0 : __ldg(sp + i);
+            }
+            cb = ncb;
+            r = rn; c0 = c0n; s0 = s0n;
+            k0 += ncommit;
+        }
+        a_my = 3;
+        if (valid && k0 + t < p.K) a_my = load_action(p, act0 + (size_t)(k0 + t) * act_stride, k0 + t, gid);
+        __syncwarp();
+    }
+
+    if (valid && t == 0) {
+        const float4 *f = s_frame + fr0 + cb * FS4;
+        const float4 l1 = f[1], l2 = f[2], l3 = f[3];
+        store_env(p, e, r, make_float4(l1.z, l1.w, l2.x, l2.y), make_float4(l2.z, l2.w, l3.x, l3.y), l3.z, l3.w);
+        if (goals_dirty) {
+            const float2 a0 = s_goal[goal0], a1 = s_goal[goal0 + 1], a2 = s_goal[goal0 + 2], a3 = s_goal[goal0 + 3], a4 = s_goal[goal0 + 4];
+            store_goals(p, e, make_float4(a0.x, a0.y, a1.x, a1.y), make_float4(a2.x, a2.y, a3.x, a3.y), make_float4(a4.x, a4.y, 0.f, 0.f));
+        }
+    }
+    __syncwarp();
+    if (lane < 8 && p.stats) {
+        const float v = stat[lane];
+        if (v != 0.f) atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * kStatLen + lane, (double)v);
+    }
+#undef stat
+}
+
+template <int T>
+static cudaError_t launch_t(const StepParams &p, cudaStream_t stream, LaunchShape *shape)
+{
+    const int envs_per_cta = (kThreads / 32) * (32 / T);
+    const int blocks = (p.N + envs_per_cta - 1) / envs_per_cta;
+    if (shape) { shape->lanes_per_env = T; shape->threads = kThreads; shape->blocks = blocks; shape->window = T; }
+    if (p.history == 2) window_kernel<T, 2><<<blocks, kThreads, 0, stream>>>(p);
+    else window_kernel<T, 1><<<blocks, kThreads, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_window(const StepParams &p, int window, cudaStream_t stream, LaunchShape *shape)
+{
+    switch (window) {
+        case 4: return launch_t<4>(p, stream, shape);
+        case 8: return launch_t<8>(p, stream, shape);
+        case 16: return launch_t<16>(p, stream, shape);
+        case 32: return launch_t<32>(p, stream, shape);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace shipsim

@@ -85,7 +85,7 @@ class BatchedShipEnv(object):
 
     def __init__(self, num_envs, game_config=None, env_config=None, device=None, seed=0, n_scenarios=1024,
                  bank=None, map_N=10, map_width_frac=0.5, auto_reset=True, honour_lidar_config=False,
-                 env_id_offset=0, lanes_per_env=0, validate_actions=True, scenario_source="host"):
+                 env_id_offset=0, lanes_per_env=0, validate_actions=True, scenario_source="host", steps_in_flight=0):
         self.knobs = snapshot(game_config, env_config, honour_lidar_config)
         if self.knobs["lidar"]["N_BEAMS"] != _abi.N_BEAMS:
             raise NotImplementedError("N_BEAMS must be 10")
@@ -120,6 +120,7 @@ class BatchedShipEnv(object):
         cfg.lidar_spread_deg = self.knobs["lidar"]["ANGULAR_SPREAD"]
         cfg.lidar_distance = self.knobs["lidar"]["DISTANCE"]
         cfg.lanes_per_env = int(lanes_per_env)
+        cfg.steps_in_flight = int(steps_in_flight)     # 0 auto, 1 serial-in-time kernel, 4/8/16/32 time-parallel window
         self.cfg = cfg
         self._h = C.c_void_p()
         _abi.check(self.L.shipsim_create(C.byref(cfg), self.device.index or 0, C.byref(self._h)))
@@ -362,7 +363,10 @@ class BatchedShipEnv(object):
         lanes, thr, ctas = C.c_int32(), C.c_int32(), C.c_int32()
         _abi.check(self.L.shipsim_launch_count(self._h, C.byref(n)))
         _abi.check(self.L.shipsim_launch_shape(self._h, C.byref(lanes), C.byref(thr), C.byref(ctas)))
-        return dict(launches=n.value, lanes_per_env=lanes.value, threads_per_cta=thr.value, ctas=ctas.value)
+        win = C.c_int32()
+        _abi.check(self.L.shipsim_launch_window(self._h, C.byref(win)))
+        return dict(launches=n.value, lanes_per_env=lanes.value, threads_per_cta=thr.value, ctas=ctas.value,
+                    steps_in_flight=win.value)
 
 
 class ShipEnv(object):
