@@ -26,11 +26,13 @@
 
 namespace shipsim {
 
+constexpr int kWinThreads = 64;      // small CTAs: a latency-bound batch is a few hundred warps, spread them evenly over the SMs
+
 template <int T, int HIST>
-__global__ void __launch_bounds__(kThreads, 4) window_kernel(const __grid_constant__ StepParams p)
+__global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int E = 32 / T;                   // envs per warp
-    constexpr int NW = kThreads / 32;
+    constexpr int NW = kWinThreads / 32;
     constexpr int OBS4 = 4 * HIST;              // float4 per obs row
     constexpr int NS = T + 1;                   // ring slots per env
     constexpr int FS4 = 5;                      // float4 per frame slot (4 used; odd stride: conflict-free)
@@ -71,10 +73,11 @@ __global__ void __launch_bounds__(kThreads, 4) window_kernel(const __grid_consta
         s_ray[32 + threadIdx.x] = p.ray_s[threadIdx.x % kBeams];
     }
     if (lane < 8) stat[lane] = 0.f;
-    const int lps_sh = p.hull_max <= 8 ? 3 : (p.hull_max <= 16 ? 4 : 5);
-    const int lps = 1 << lps_sh, nslots = 32 >> lps_sh;
-    const int sslot = lane >> lps_sh, sel = lane & (lps - 1);
-    const unsigned slotmask = lps == 32 ? kFull : (((1u << lps) - 1u) << (sslot * lps));
+    // separating-axis pass: 4 steps at a time, 8 lanes each; a lane takes every 8th edge of the bank
+    constexpr int lps = 8, nslots = 4;
+    const int sslot = lane >> 3, sel = lane & 7;
+    const unsigned slotmask = 0xffu << (sslot * 8);
+    const int epl = (p.hull_max + lps - 1) / lps;
 
     const size_t act_esize = p.action_dtype == 1 ? 8 : (p.action_dtype == 2 ? 1 : 4);
     const char *act0 = reinterpret_cast<const char *>(p.actions) + (size_t)ec * act_esize;
@@ -127,18 +130,22 @@ __global__ void __launch_bounds__(kThreads, 4) window_kernel(const __grid_consta
         int mrud;
         {
             float4 *ph = s_ph + (warp * 32 + gbase) * 2;
-            // scan 1: rudder, angular velocity, angle (these do not depend on the trig of the pose)
+            // scan 1: rudder, angular velocity, angle (these do not depend on the trig of the pose).  The action is
+            // decoded once per lane: low byte = rudder increment + 5 (Ship.rotate, models.py:136-146), bit 8 = thrust.
             {
+                const int dec = (a_my == 1 ? 0 : (a_my == 2 ? 10 : 5)) | (a_my == 0 ? 256 : 0);
                 float th = r.th, w = r.w;
                 int rud = r.rudder;
+                float4 *po = ph;
 #pragma unroll 4
                 for (int i = 0; i < T; ++i) {
-                    const int a = __shfl_sync(kFull, a_my, gbase + i);
-                    const float dw = a == 0 ? -p.ang_dt * (float)rud : 0.f;
-                    rud = a == 1 ? max(rud - 5, -10) : (a == 2 ? min(rud + 5, 10) : rud);
+                    const int d = __shfl_sync(kFull, dec, gbase + i);
+                    const float dw = (d & 256) ? -p.ang_dt * (float)rud : 0.f;
+                    rud = min(max(rud + (d & 255) - 5, -10), 10);    // clamp_rudder: rud is always within [-10, 10]
                     th += w * p.dt;
                     w = w * p.damping + dw;
-                    if (t == 0) ph[2 * i] = make_float4(th, w, __int_as_float(rud), 0.f);
+                    if (t == 0) *po = make_float4(th, w, __int_as_float(rud), 0.f);
+                    po += 2;
                 }
             }
             __syncwarp();
@@ -155,6 +162,7 @@ __global__ void __launch_bounds__(kThreads, 4) window_kernel(const __grid_consta
             // scan 2: velocity and position
             {
                 float x = r.x, y = r.y, vx = r.vx, vy = r.vy;
+                float4 *po = ph + 1;
 #pragma unroll 4
                 for (int i = 0; i < T; ++i) {
                     const float dvx = __shfl_sync(kFull, dvx_t, gbase + i), dvy = __shfl_sync(kFull, dvy_t, gbase + i);
@@ -162,7 +170,8 @@ __global__ void __launch_bounds__(kThreads, 4) window_kernel(const __grid_consta
                     y += vy * p.dt;
                     vx = vx * p.damping + dvx;
                     vy = vy * p.damping + dvy;
-                    if (t == 0) ph[2 * i + 1] = make_float4(x, y, vx, vy);
+                    if (t == 0) *po = make_float4(x, y, vx, vy);
+                    po += 2;
                 }
             }
             __syncwarp();
@@ -273,18 +282,36 @@ __global__ void __launch_bounds__(kThreads, 4) window_kernel(const __grid_consta
                 for (int b = 0; b < 2; ++b) {
                     const bool do_b = act_env && ((bsa >> (28 + b)) & 1u) && !coll;
                     const int nb = __float_as_int(b ? hdr.w : hdr.z);
-                    const bool actl = do_b && sel < nb;
-                    float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (actl) ed = __ldg(bE + b * p.maxv + sel);
-                    const unsigned sb = __ballot_sync(kFull, actl && bank_axis_separates(ed, rx, ry, bx, by));
+                    const float4 *bEb = bE + b * p.maxv;
+                    // a bank edge normal separates?  (lane `sel` of the slot takes edges sel, sel + 8, ...)
+                    bool lsep = false;
+#pragma unroll 1
+                    for (int u = 0; u < epl; ++u) {
+                        const int idx = sel + u * lps;
+                        if (do_b && idx < nb) lsep = lsep || bank_axis_separates(__ldg(bEb + idx), rx, ry, bx, by);
+                    }
+                    const unsigned sb = __ballot_sync(kFull, lsep);
                     bool sep = (sb & slotmask) != 0u;
-                    if (__ballot_sync(kFull, do_b && !sep)) {
+                    if (__ballot_sync(kFull, do_b && !sep)) {                   // else try the ship's edge normals
+                        float pr[kShipVerts];
+#pragma unroll
+                        for (int j = 0; j < kShipVerts; ++j) pr[j] = 3.0e38f;
+#pragma unroll 1
+                        for (int u = 0; u < epl; ++u) {
+                            const int idx = sel + u * lps;
+                            if (do_b && idx < nb) {
+                                const float4 ed = __ldg(bEb + idx);
+#pragma unroll
+                                for (int j = 0; j < kShipVerts; ++j) {
+                                    const float nx = p.ship_nx[j] * bc - p.ship_ny[j] * bs;
+                                    const float ny = p.ship_nx[j] * bs + p.ship_ny[j] * bc;
+                                    pr[j] = fminf(pr[j], nx * (ed.z - bx) + ny * (ed.w - by));
+                                }
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < kShipVerts; ++j) {
-                            const float nx = p.ship_nx[j] * bc - p.ship_ny[j] * bs;
-                            const float ny = p.ship_nx[j] * bs + p.ship_ny[j] * bc;
-                            const float pr = actl ? nx * (ed.z - bx) + ny * (ed.w - by) : 3.0e38f;
-                            const int mn = __reduce_min_sync(slotmask, f2ord(pr));
+                            const int mn = __reduce_min_sync(slotmask, f2ord(pr[j]));
                             sep = sep || (mn > f2ord(p.ship_off[j]));
                         }
                     }
@@ -360,15 +387,13 @@ __global__ void __launch_bounds__(kThreads, 4) window_kernel(const __grid_consta
         const bool do_reset = p.auto_reset && dmask != 0u;
         const int ncommit = do_reset ? __ffs(dmask) - gbase : nvalid;
         const bool commit = t < ncommit;
-        // episode return: ordered sum, same rounding as one step at a time
-        float my_ret = 0.f;
-        {
-            float acc = r.ret;
+        // episode return after step t: ordered sum (lane t adds the rewards of steps 0..t one by one), same rounding
+        // as one step at a time
+        float my_ret = r.ret;
 #pragma unroll 8
-            for (int i = 0; i < T; ++i) {
-                acc += __shfl_sync(kFull, reward, gbase + i);
-                if (i == t) my_ret = acc;
-            }
+        for (int i = 0; i < T; ++i) {
+            const float rv = __shfl_sync(kFull, reward, gbase + i);
+            if (i <= t) my_ret += rv;
         }
         if (commit) {
             if (goal_reached) atomicAdd(stat + 3, 1.f);
@@ -517,11 +542,11 @@ __global__ void __launch_bounds__(kThreads, 4) window_kernel(const __grid_consta
 template <int T>
 static cudaError_t launch_t(const StepParams &p, cudaStream_t stream, LaunchShape *shape)
 {
-    const int envs_per_cta = (kThreads / 32) * (32 / T);
+    const int envs_per_cta = (kWinThreads / 32) * (32 / T);
     const int blocks = (p.N + envs_per_cta - 1) / envs_per_cta;
-    if (shape) { shape->lanes_per_env = T; shape->threads = kThreads; shape->blocks = blocks; shape->window = T; }
-    if (p.history == 2) window_kernel<T, 2><<<blocks, kThreads, 0, stream>>>(p);
-    else window_kernel<T, 1><<<blocks, kThreads, 0, stream>>>(p);
+    if (shape) { shape->lanes_per_env = T; shape->threads = kWinThreads; shape->blocks = blocks; shape->window = T; }
+    if (p.history == 2) window_kernel<T, 2><<<blocks, kWinThreads, 0, stream>>>(p);
+    else window_kernel<T, 1><<<blocks, kWinThreads, 0, stream>>>(p);
     return cudaGetLastError();
 }
 
