@@ -34,6 +34,13 @@ def b_alg(K):
     return 137.0 + 188.0 / K
 
 
+def kernel_name(info):
+    """The kernel the last launch ran: the time-parallel window kernel (small batches) or the serial-in-time one."""
+    if info.get("steps_in_flight", 1) > 1:
+        return "window_kernel<T=%d>" % info["steps_in_flight"]
+    return "step_kernel<G=%d>" % info["lanes_per_env"]
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -247,7 +254,7 @@ def main():
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": "step_kernel", "bytes_per_env_step": b_alg(ROLLOUT),
+                "peak_source": peak_src, "kernel": kernel_name(env.launch_info()), "bytes_per_env_step": b_alg(ROLLOUT),
                 "launch_ms": launch_ms}
 
     # ---- end to end through the C ABI with HOST buffers (copies inside the timed region)

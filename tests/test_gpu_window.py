@@ -142,12 +142,14 @@ def test_auto_selection():
     e = _env(256, bank)
     e.reset()
     e.rollout(None, K=16)
-    assert e.launch_info()["steps_in_flight"] == 8
+    assert e.launch_info()["steps_in_flight"] == 1            # fewer steps than the window (32 for so few envs)
+    e.rollout(None, K=40)
+    assert e.launch_info()["steps_in_flight"] == 32
     e.step(torch.zeros(256, dtype=torch.int32, device="cuda"))
     assert e.launch_info()["steps_in_flight"] == 1
     e2 = _env(256, bank, lanes_per_env=8)
     e2.reset()
-    e2.rollout(None, K=16)
+    e2.rollout(None, K=40)
     assert e2.launch_info()["steps_in_flight"] == 1
     with pytest.raises(ValueError):
         _env(16, bank, steps_in_flight=5)
