@@ -127,9 +127,11 @@ __device__ __forceinline__ int random_action(const StepParams &p, long long gid,
 // Cody-Waite reduction by pi/2 (3 constants, exact for |x| < ~1e5, which bounds any reachable angle:
 // |w| <= ~1.4 rad/s * dt over at most max_steps steps) + the usual minimax polynomials on [-pi/4, pi/4];
 // ~1 ulp, no local-memory slow path in the hot loop (libdevice's Payne-Hanek branch is kept for huge angles).
+static __device__ __noinline__ void sincos_huge(float x, float *sn, float *cs) { sincosf(x, sn, cs); }   // never in practice: keep it out of the loop body
+
 __device__ __forceinline__ void sincos_fast(float x, float &sn, float &cs)
 {
-    if (fabsf(x) > 1.0e5f) { sincosf(x, &sn, &cs); return; }
+    if (fabsf(x) > 1.0e5f) { sincos_huge(x, &sn, &cs); return; }
     const float q = rintf(x * 0.636619772367581343f);          // 2/pi
     float r = fmaf(q, -1.57079601287841796875f, x);
     r = fmaf(q, -3.1391647326017846353352069854736e-07f, r);
@@ -241,6 +243,21 @@ __device__ __forceinline__ bool goal_touches_ship(const StepParams &p, float qx,
         best = fminf(best, cx * cx + cy * cy);
     }
     return !outside || best <= p.goal_r * p.goal_r;
+}
+
+// The same contact test with the clear cases settled first: the largest signed distance m of the goal centre to the
+// hull's edge lines decides "centre well inside the hull" (m < -eps: contact) and "farther than the goal radius from
+// some edge line" (m > r + eps: no contact, the true distance is at least m); eps = 1e-3 is orders of magnitude above
+// fp32 rounding at these magnitudes, so both shortcuts agree with the full test, which decides everything else.
+__device__ __forceinline__ bool goal_contact(const StepParams &p, float qx, float qy)
+{
+    float m = -3.0e38f;
+#pragma unroll
+    for (int j = 0; j < kShipVerts; ++j)
+        m = fmaxf(m, p.ship_nx[j] * (qx - p.ship_lx[j]) + p.ship_ny[j] * (qy - p.ship_ly[j]));
+    if (m < -1.0e-3f) return true;
+    if (m > p.goal_r + 1.0e-3f) return false;
+    return !goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy);
 }
 
 __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }

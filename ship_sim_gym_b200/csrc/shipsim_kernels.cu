@@ -209,31 +209,25 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                 gd2[i] = ux * ux + uy * uy;
             }
             if (G == 1) {
-                // throughput-bound batches: nearest alive goal first (needed for the frame anyway); nothing can touch the
-                // hull unless that one is inside the bounding circle
+                // throughput-bound batches: goals inside the hull's bounding circle are tested one per loop trip (a lane
+                // rarely has more than one), then the nearest REMAINING goal is picked once for the frame
+                unsigned cand = 0u;
+#pragma unroll
+                for (int i = 0; i < kGoals; ++i)
+                    if (valid && ((r.alive >> i) & 1) && gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
+#pragma unroll 1
+                while (cand) {
+                    const int i = __ffs(cand) - 1;
+                    cand &= cand - 1u;
+                    const float2 gi = s_goal[goal0 + i * EPW];
+                    const float ux = gi.x - r.x, uy = gi.y - r.y;
+                    const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
+                    if (goal_contact(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << i); }
+                }
                 float best = 3.0e38f;
 #pragma unroll
                 for (int i = 0; i < kGoals; ++i)
                     if (((r.alive >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
-                if (valid && best <= p.goal_cull_r2) {           // rare: some goal is within reach of the hull
-#pragma unroll 1
-                    for (int i = 0; i < kGoals; ++i) {
-                        if (!((r.alive >> i) & 1)) continue;
-                        float ux = g[0].x, uy = g[0].y, dd = gd2[0];
-#pragma unroll
-                        for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; dd = gd2[j]; }
-                        if (dd > p.goal_cull_r2) continue;
-                        ux -= r.x; uy -= r.y;
-                        const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
-                        if (!goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << i); }
-                    }
-                    if (goal_reached) {                         // the nearest REMAINING goal goes into the frame
-                        best = 3.0e38f; gx = -1.f; gy = -1.f;
-#pragma unroll
-                        for (int i = 0; i < kGoals; ++i)
-                            if (((r.alive >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
-                    }
-                }
             } else {
                 // latency-bound batches: independent per-goal culls (no dependent chain before the branch)
                 unsigned cand = 0u;
@@ -248,7 +242,7 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                     for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
                     ux -= r.x; uy -= r.y;
                     const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
-                    if (!goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << i); }
+                    if (goal_contact(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << i); }
                 }
                 float best = 3.0e38f;
 #pragma unroll

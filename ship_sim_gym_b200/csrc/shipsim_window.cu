@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
     __shared__ float2 s_goal[NW * E * kGoals];
     __shared__ float4 s_rf[NW * E * 2];         // reset frame, first two float4 (the rest is -1)
     __shared__ float4 s_ph[NW * 32 * 2];        // physics scan -> lanes: (th, w, bits(rudder), -) and (x, y, vx, vy) per step
+    __shared__ int4 s_env[NW * E];              // per env, for the copy-out: step cursor, committed steps, carry slot, reset?
     __shared__ float s_ray[2 * 32];
     __shared__ unsigned s_src[NW][32];          // ray pass: compacted (plane row | frame offset) of the needy steps
     __shared__ float s_stat[NW][8];
@@ -208,15 +209,14 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < kGoals; ++i)
                 if (active && ((r.alive >> i) & 1) && gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
+#pragma unroll 1
             while (cand) {
                 const int i = __ffs(cand) - 1;
                 cand &= cand - 1u;
-                float ux = g[0].x, uy = g[0].y;
-#pragma unroll
-                for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
-                ux -= mx; uy -= my;
+                const float2 gi = s_goal[goal0 + i];
+                const float ux = gi.x - mx, uy = gi.y - my;
                 const float qx = ux * mc + uy * ms, qy = -ux * ms + uy * mc;
-                if (!goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy)) touch |= 1u << i;
+                if (goal_contact(p, qx, qy)) touch |= 1u << i;
             }
         }
         // this step's lidar slots: "no hit" until the ray pass says otherwise
@@ -242,9 +242,16 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
         // ---- plane phase at pose t: lidar planes of step t+1 + ship-vs-bank pre-test of step t
         cp_async_wait_all();
         unsigned ask = 0u;
-        if (staged) ask = plane_phase<true, true>(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow, myrow + 1);
-        else if (near_any) ask = plane_phase<true, false>(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow);
-        else if (active) myrow[0] = make_float4(mc, ms, 0.f, 0.f);
+        if (staged) {
+            ask = plane_phase<true, true>(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow, myrow + 1);
+        } else if (near_any) {                  // more candidates than a row holds: rays are cast serially, full SAT pass
+            myrow[0] = make_float4(mc, ms, __int_as_float(kHdrBig), 0.f);
+            myrow[1] = make_float4(mx, my, hx, hy);
+            myrow[2] = make_float4(__int_as_float(r.scen), __uint_as_float(cell.x), __uint_as_float(cell.y), __uint_as_float(cell.z));
+            ask = ((cell.x != 0u || (cell.z & 1u)) ? 1u : 0u) | ((cell.y != 0u || (cell.z & 2u)) ? 2u : 0u);
+        } else if (active) {
+            myrow[0] = make_float4(mc, ms, 0.f, 0.f);
+        }
         __syncwarp();
 
         // ---- overlap test at the new pose -> collide_ship (game.py:232-241): separating-axis pass for the steps the
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
                     ry[j] = p.ship_lx[j] * bs + p.ship_ly[j] * bc;
                 }
                 bool coll = false;
-#pragma unroll
+#pragma unroll 1
                 for (int b = 0; b < 2; ++b) {
                     const bool do_b = act_env && ((bsa >> (28 + b)) & 1u) && !coll;
                     const int nb = __float_as_int(b ? hdr.w : hdr.z);
@@ -440,15 +447,21 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
             myfr[3] = make_float4(h[6], h[7], h[8], h[9]);
         }
 
-        // ---- 4. the state the next window starts from: after the last committed step, or the reset
+        // ---- 4. the state the next window starts from: after the last committed step (the scans left it in shared
+        // memory), or the reset
         const int srcl = gbase + max(ncommit, 1) - 1;
         EnvRegs rn;
-        rn.x = __shfl_sync(kFull, mx, srcl); rn.y = __shfl_sync(kFull, my, srcl); rn.th = __shfl_sync(kFull, mth, srcl);
-        rn.vx = __shfl_sync(kFull, mvx, srcl); rn.vy = __shfl_sync(kFull, mvy, srcl); rn.w = __shfl_sync(kFull, mw, srcl);
+        {
+            const float4 *ph = s_ph + (warp * 32 + srcl) * 2;
+            const float4 v0 = ph[0], v1 = ph[1];
+            rn.th = v0.x; rn.w = v0.y; rn.rudder = __float_as_int(v0.z);
+            rn.x = v1.x; rn.y = v1.y; rn.vx = v1.z; rn.vy = v1.w;
+        }
         rn.ret = __shfl_sync(kFull, my_ret, srcl);
-        rn.rudder = __shfl_sync(kFull, mrud, srcl); rn.alive = __shfl_sync(kFull, alive_t, srcl);
+        rn.alive = __shfl_sync(kFull, alive_t, srcl);
         rn.steps = r.steps + ncommit; rn.scen = r.scen; rn.episode = r.episode;
         float c0n = __shfl_sync(kFull, mc, srcl), s0n = __shfl_sync(kFull, ms, srcl);
+        if (t == 0) s_env[warp * E + el] = make_int4(k0, ncommit, cb, (int)do_reset);
         if (do_reset) {                                             // ShipEnv.reset (ship_env.py:171-184)
             const int ep = r.episode + 1;
             reset_env(p, rn, pick_scenario(p, gid, ep), ep);
@@ -474,20 +487,18 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
             const float4 neg = make_float4(-1.f, -1.f, -1.f, -1.f);
             const int col = lane % OBS4;
             const int half = HIST == 2 ? (col >> 2) : 1, q = col & 3;
-#pragma unroll
+#pragma unroll 2
             for (int i = 0; i < OBS4; ++i) {
                 const int ridx = lane / OBS4 + i * (32 / OBS4);     // the row's owner lane
-                const int k0r = __shfl_sync(kFull, k0, ridx), ncr = __shfl_sync(kFull, ncommit, ridx);
-                const int cbr = __shfl_sync(kFull, cb, ridx);
-                const int rsr = __shfl_sync(kFull, (int)do_reset, ridx);
                 const int elr = ridx / T, tr = ridx % T;
-                if (tr < ncr) {
+                const int4 ev = s_env[warp * E + elr];              // k0, committed, carry slot, reset
+                if (tr < ev.y) {
                     float4 v;
-                    if (rsr && tr == ncr - 1)                       // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
+                    if (ev.w && tr == ev.y - 1)                     // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
                         v = (half == 0 || q >= 2) ? neg : s_rf[(warp * E + elr) * 2 + q];
                     else
-                        v = s_frame[wfr0 + elr * FR4 + ring(cbr + tr + half) * FS4 + q];
-                    __stcs(p.obs + ((size_t)(k0r + tr) * p.N + (warp_env0 + elr)) * OBS4 + col, v);
+                        v = s_frame[wfr0 + elr * FR4 + ring(ev.z + tr + half) * FS4 + q];
+                    __stcs(p.obs + ((size_t)(ev.x + tr) * p.N + (warp_env0 + elr)) * OBS4 + col, v);
                 }
             }
         }
