@@ -187,6 +187,12 @@ int shipsim_set_state(shipsim_t *h, const float *host_pose, const int32_t *host_
 int shipsim_get_state(shipsim_t *h, float *host_pose, int32_t *host_ints, float *host_lidar, float *host_goals,
                       float *host_ep_return);
 
+/* Debug rendering of ONE env into dev_rgb[height][width][3] (uint8, device memory): replaces ShipGame.render +
+ * get_screen (game.py:133-138,197-229), i.e. the `rgb_array` mode ShipEnv.metadata lists (ship_env.py:18).  Blue
+ * background, banks, remaining goals, the hull, a circle per lidar ray where it ended (red = has hit, green = full
+ * length) and the yellow position marker; screen y points down as in pygame.  Enqueued on `stream`. */
+int shipsim_render(shipsim_t *h, int32_t env_index, int32_t width, int32_t height, uint8_t *dev_rgb, void *stream);
+
 /* Introspection for benchmarks: launches issued so far, lanes per env and CTA size actually used. */
 int shipsim_launch_count(const shipsim_t *h, int64_t *out);
 int shipsim_launch_shape(const shipsim_t *h, int32_t *lanes_per_env, int32_t *threads_per_cta, int32_t *ctas);

@@ -581,6 +581,17 @@ extern "C" int shipsim_get_state(shipsim_t *h, float *pose, int32_t *ints, float
     return SHIPSIM_OK;
 }
 
+extern "C" int shipsim_render(shipsim_t *h, int32_t env_index, int32_t width, int32_t height, uint8_t *dev_rgb, void *stream)
+{
+    const int rc = ready(h);
+    if (rc) return rc;
+    if (env_index < 0 || env_index >= h->cfg.num_envs) return fail(SHIPSIM_ERR_ARG, "env_index out of range");
+    if (width < 1 || height < 1 || !dev_rgb) return fail(SHIPSIM_ERR_ARG, "bad image size / NULL buffer");
+    DeviceGuard g(h->device);
+    CU(launch_render(h->p, env_index, width, height, dev_rgb, (cudaStream_t)stream));
+    return SHIPSIM_OK;
+}
+
 extern "C" int shipsim_launch_count(const shipsim_t *h, int64_t *out)
 {
     if (!h || !out) return fail(SHIPSIM_ERR_ARG, "NULL argument");

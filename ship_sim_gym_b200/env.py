@@ -207,9 +207,23 @@ class BatchedShipEnv(object):
         self.action_space.seed(seed)
         return [seed]
 
-    def render(self, mode="human", close=False):
-        """ship_env.py:158-168 prints the last action and return; drawing is out of scope for the batch."""
-        return None
+    def render(self, mode="human", close=False, env_index=0, size=None):
+        """ship_env.py:158-168 only prints; `rgb_array` (listed in metadata, ship_env.py:18, never implemented there)
+        draws ONE env on the device the way ShipGame.render does (game.py:197-229) and returns a uint8 CUDA tensor
+        [height, width, 3] (the gym convention); `size` = (width, height), default = BOUNDS."""
+        if mode != "rgb_array":
+            return None
+        if self._needs_reset:
+            raise _abi.ShipsimError("call reset() before render()")
+        w, h = (int(self.knobs["W"]), int(self.knobs["H"])) if size is None else (int(size[0]), int(size[1]))
+        img = torch.empty(h, w, 3, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _abi.check(self.L.shipsim_render(self._h, int(env_index), w, h, img.data_ptr(), self._stream()))
+        return img
+
+    def get_screen(self, env_index=0):
+        """ShipGame.get_screen (game.py:133-138): pygame.surfarray.array3d layout, [width, height, 3]."""
+        return self.render("rgb_array", env_index=env_index).permute(1, 0, 2).contiguous()
 
     # ------------------------------------------------------------------------------------------ reset / step
     def reset(self, mask=None, scenario=None):
@@ -414,6 +428,8 @@ class ShipEnv(object):
         return obs[0].cpu().numpy(), self.reward, bool(done[0]), {}
 
     def render(self, mode="human", close=False):
+        if mode == "rgb_array":
+            return self.batch.render("rgb_array").cpu().numpy()
         import sys
         if self.last_action is not None:
             sys.stdout.write("action=%s, cumm_reward=%s" % (self.last_action, self.cumulative_reward))

@@ -150,3 +150,38 @@ def test_curriculum_driver_on_a_live_batch():
     with pytest.raises(ValueError):
         env.set_max_steps(0)
     env.close()
+
+
+def test_rgb_array_render_of_one_env():
+    """`rgb_array` rendering of a selected env (ShipGame.render / get_screen, game.py:133-138,197-229)."""
+    import numpy as np
+    from ship_sim_gym_b200 import BatchedShipEnv, ShipEnv
+    from ship_sim_gym_b200.config import EnvConfig, GameConfig
+    env = BatchedShipEnv(64, seed=1)
+    obs = env.reset()
+    img = env.render("rgb_array", env_index=5).cpu().numpy()
+    assert img.shape == (600, 600, 3) and img.dtype == np.uint8
+    assert env.get_screen(5).shape == (600, 600, 3)
+    assert env.render() is None                                  # `human` mode only prints in the reference
+    # the yellow marker sits on the spawn point (300, 25): screen y points down
+    assert tuple(img[600 - 25, 300]) == (255, 255, 0)
+    # water far from everything is the reference's background colour
+    st = env.get_state()
+    assert tuple(img[600 - 300, 300]) in ((0, 0, 200), (0, 200, 0))
+    # each remaining goal shows as a green disc
+    gx, gy = st["goals"][5, 2]
+    assert tuple(img[int(round(600 - gy)) - 1, int(gx)]) == (0, 200, 0)
+    # the left bank hugs x = 0 somewhere along the river, the hull is white just above the marker
+    assert (img[:, 2] == np.array([110, 110, 110])).all(-1).any()
+    assert tuple(img[600 - 25 - 20, 300 + 10]) == (255, 255, 255)
+    # after some steps the picture follows the state
+    import torch
+    env.rollout(torch.zeros(40, 64, dtype=torch.int32, device=env.device))
+    st = env.get_state()
+    img2 = env.render("rgb_array", env_index=5, size=(300, 300)).cpu().numpy()
+    x, y = st["pose"][5, :2]
+    if 0 < x < 600 and 0 < y < 600:
+        assert tuple(img2[min(299, int((600 - y) / 2)), min(299, int(x / 2))]) == (255, 255, 0)
+    single = ShipEnv(GameConfig, EnvConfig)
+    single.reset()
+    assert single.render("rgb_array").shape == (600, 600, 3)
