@@ -19,6 +19,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+    os.environ["NCCL_DEBUG"] = "WARN"        # NCCL's version banner goes to stdout: rank 0 prints ONE JSON line
 
 ENVS = 4096          # BASELINE.json configs[1]
 ROLLOUT = 1000       # env-steps per launch ("1,000 steps")
