@@ -308,8 +308,9 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                                 const float nx = p.ship_nx[j] * bc - p.ship_ny[j] * bs;
                                 const float ny = p.ship_nx[j] * bs + p.ship_ny[j] * bc;
                                 const float pr = actl ? nx * (ed.z - bx) + ny * (ed.w - by) : 3.0e38f;
-                                const int mn = __reduce_min_sync(slotmask, f2ord(pr));
-                                sep = sep || (mn > f2ord(p.ship_off[j]));
+                                // axis j separates <=> no bank vertex of the slot reaches the hull's plane j
+                                const unsigned reach = __ballot_sync(kFull, pr <= p.ship_off[j]);
+                                sep = sep || (reach & slotmask) == 0u;
                             }
                         }
                         if (do_b && !sep) coll = true;

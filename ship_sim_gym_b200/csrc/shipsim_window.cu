@@ -317,9 +317,9 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < kShipVerts; ++j) {
-                            const int mn = __reduce_min_sync(slotmask, f2ord(pr[j]));
-                            sep = sep || (mn > f2ord(p.ship_off[j]));
+                        for (int j = 0; j < kShipVerts; ++j) {      // axis j separates <=> no bank vertex of the slot reaches the hull's plane j
+                            const unsigned reach = __ballot_sync(kFull, pr[j] <= p.ship_off[j]);
+                            sep = sep || (reach & slotmask) == 0u;
                         }
                     }
                     if (do_b && !sep) coll = true;
@@ -373,14 +373,17 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
         }
 
         // ---- 3. the sequential leftovers.  Goals taken so far in the window: prefix OR of the touch masks.
-        unsigned inc = touch;
+        // (one ballot per goal: taken before / up to step t <=> an earlier / this-or-earlier lane of the env touches it)
+        unsigned inc = 0u, exc = 0u;
+        {
+            const unsigned below = segmask & ((1u << lane) - 1u), upto = segmask & ((2u << lane) - 1u);
 #pragma unroll
-        for (int d = 1; d < T; d <<= 1) {
-            const unsigned o = __shfl_up_sync(kFull, inc, d, T);
-            if (t >= d) inc |= o;
+            for (int i = 0; i < kGoals; ++i) {
+                const unsigned m = __ballot_sync(kFull, (touch >> i) & 1u);
+                if (m & below) exc |= 1u << i;
+                if (m & upto) inc |= 1u << i;
+            }
         }
-        unsigned exc = __shfl_up_sync(kFull, inc, 1, T);
-        if (t == 0) exc = 0u;
         const int alive_prev = r.alive & ~(int)exc, alive_t = r.alive & ~(int)inc;
         const bool goal_reached = (alive_prev & (int)touch) != 0;
         const int steps_t = r.steps + t + 1;
@@ -484,21 +487,24 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
         // ---- outputs of the committed steps.  Obs row of step t = [frame t-1 | frame t] = ring slots (cb+t, cb+t+1);
         // OBS4 lanes per row, 32/OBS4 rows per round, 128-bit streaming stores.
         if (p.obs) {
+            constexpr int RPR = 32 / OBS4;                          // rows per round
             const float4 neg = make_float4(-1.f, -1.f, -1.f, -1.f);
-            const int col = lane % OBS4;
+            const int col = lane % OBS4, r0 = lane / OBS4;
             const int half = HIST == 2 ? (col >> 2) : 1, q = col & 3;
-#pragma unroll 2
-            for (int i = 0; i < OBS4; ++i) {
-                const int ridx = lane / OBS4 + i * (32 / OBS4);     // the row's owner lane
-                const int elr = ridx / T, tr = ridx % T;
+            const size_t rstride = (size_t)p.N * OBS4;              // float4 between consecutive steps of one env
+#pragma unroll 1
+            for (int elr = 0; elr < E; ++elr) {
                 const int4 ev = s_env[warp * E + elr];              // k0, committed, carry slot, reset
-                if (tr < ev.y) {
-                    float4 v;
-                    if (ev.w && tr == ev.y - 1)                     // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
-                        v = (half == 0 || q >= 2) ? neg : s_rf[(warp * E + elr) * 2 + q];
-                    else
-                        v = s_frame[wfr0 + elr * FR4 + ring(ev.z + tr + half) * FS4 + q];
-                    __stcs(p.obs + ((size_t)(ev.x + tr) * p.N + (warp_env0 + elr)) * OBS4 + col, v);
+                const int last = ev.w ? ev.y - 1 : -1;              // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
+                const float4 rfv = (half == 0 || q >= 2) ? neg : s_rf[(warp * E + elr) * 2 + q];
+                const float4 *fb = s_frame + wfr0 + elr * FR4 + q;
+                float4 *o = p.obs + ((size_t)(ev.x + r0) * p.N + (warp_env0 + elr)) * OBS4 + col;
+                int slot = ring(ev.z + r0 + half);
+                for (int tr = r0; tr < ev.y; tr += RPR) {
+                    __stcs(o, tr == last ? rfv : fb[slot * FS4]);
+                    o += rstride * RPR;
+                    slot += RPR;
+                    if (slot >= NS) slot -= NS;
                 }
             }
         }
