@@ -280,7 +280,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e = {"value": float(ENVS) * ROLLOUT * e2e_steps * world / float(t.item()), "unit": UNIT,
            "h2d_bytes_per_step": int(h_act.numel() * 4),
-           "d2h_bytes_per_step": int(h_obs.numel() * 4 + h_rew.numel() * 4 + h_done.numel()),
+           # HISTORY_SIZE = 2: only the frames cross PCIe (64 B per env-step + the frame of the state before the call);
+           # shipsim_step_host rebuilds the 128-byte [previous | current] rows in the caller's buffer with host threads
+           "d2h_bytes_per_step": int(h_obs.numel() * 2 + ENVS * 64 + h_rew.numel() * 4 + h_done.numel()),
+           "host_obs_bytes_per_step": int(h_obs.numel() * 4),
            "steps": e2e_steps, "api": "BatchedShipEnv.step_host -> shipsim_step_host (pinned host buffers)"}
 
     # ---- extra configurations (not the headline; same kernel)

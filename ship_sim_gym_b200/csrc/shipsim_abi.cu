@@ -3,15 +3,76 @@
 #include "../../include/shipsim.h"
 #include "shipsim_device.cuh"
 #include "shipsim_launch.h"
+#include "shipsim_host.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 using namespace shipsim;
+
+// Small persistent worker pool for the host half of shipsim_step_host (assembling observation histories from frames
+// while later chunks are still crossing PCIe).  run(n, fn) calls fn(i) for i in [0, n) on the workers + the caller.
+class HostPool {
+public:
+    explicit HostPool(int n_threads)
+    {
+        for (int i = 0; i < n_threads; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~HostPool()
+    {
+        { std::lock_guard<std::mutex> lk(m_); quit_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto &t : workers_) t.join();
+    }
+    void run(int n, const std::function<void(int)> &fn)
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn; n_ = n; next_.store(0); pending_ = (int)workers_.size(); ++gen_;
+        }
+        cv_.notify_all();
+        drain();
+        std::unique_lock<std::mutex> lk(m_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+    }
+    int size() const { return (int)workers_.size() + 1; }
+
+private:
+    void drain() { for (int i; (i = next_.fetch_add(1)) < n_;) (*fn_)(i); }
+    void loop()
+    {
+        unsigned seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (quit_) return;
+            }
+            drain();
+            { std::lock_guard<std::mutex> lk(m_); --pending_; }
+            done_cv_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_ = 0, pending_ = 0;
+    unsigned gen_ = 0;
+    bool quit_ = false;
+};
 
 struct shipsim_handle {
     shipsim_config cfg;
@@ -30,7 +91,13 @@ struct shipsim_handle {
     int32_t *d_act = nullptr; float *d_obs = nullptr; float *d_rew = nullptr; uint8_t *d_done = nullptr;
     int stage_K = 0;
     cudaStream_t copy_stream = nullptr;      // shipsim_step_host: results of chunk i go home while chunk i+1 is computed
-    cudaEvent_t chunk_done[2] = {nullptr, nullptr};
+    static constexpr int kMaxChunks = 64;
+    cudaEvent_t chunk_done[kMaxChunks] = {}, copy_done[kMaxChunks] = {};
+    float *h_frames = nullptr;               // pinned staging: frame of the state before the call + one frame per env-step
+    uint8_t *h_done = nullptr;               // pinned staging for the done flags when the caller does not want them
+    size_t h_frames_cap = 0, h_done_cap = 0;
+    float4 *d_frame0 = nullptr;
+    HostPool *pool = nullptr;
     int64_t launches = 0;
     LaunchShape shape{1, kThreads, 0, 1};
 };
@@ -232,6 +299,11 @@ extern "C" int shipsim_destroy(shipsim_t *h)
     DeviceGuard g(h->device);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto &ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : h->copy_done) if (ev) cudaEventDestroy(ev);
+    if (h->h_frames) cudaFreeHost(h->h_frames);
+    if (h->h_done) cudaFreeHost(h->h_done);
+    cudaFree(h->d_frame0);
+    delete h->pool;
     cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_spawn); cudaFree(h->d_act);
     cudaFree(h->d_gen_xy); cudaFree(h->d_gen_goals); cudaFree(h->d_gen_n); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
     delete h;
@@ -445,8 +517,8 @@ extern "C" int shipsim_reset(shipsim_t *h, const uint8_t *dev_mask, const int32_
     return SHIPSIM_OK;
 }
 
-extern "C" int shipsim_step(shipsim_t *h, const void *dev_actions, int action_dtype, int32_t K, float *dev_obs, float *dev_reward,
-                            uint8_t *dev_done, void *stream)
+static int step_impl(shipsim_t *h, const void *dev_actions, int action_dtype, int32_t K, float *dev_obs, float *dev_reward,
+                     uint8_t *dev_done, void *stream, int history)
 {
     const int rc = ready(h);
     if (rc) return rc;
@@ -458,12 +530,19 @@ extern "C" int shipsim_step(shipsim_t *h, const void *dev_actions, int action_dt
     StepParams p = h->p;
     p.actions = dev_actions; p.action_dtype = action_dtype; p.K = K;
     p.obs = (float4 *)dev_obs; p.reward = dev_reward; p.done = dev_done;
+    p.history = history;
     // the window kernel needs the actions of the whole rollout up front and at least one full window of steps
     if (h->window > 1 && K >= h->window) CU(launch_window(p, h->window, (cudaStream_t)stream, &h->shape));
     else CU(launch_step(p, h->lanes, (cudaStream_t)stream, &h->shape));
     h->p.step0 += (unsigned)K;
     h->launches++;
     return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_step(shipsim_t *h, const void *dev_actions, int action_dtype, int32_t K, float *dev_obs, float *dev_reward,
+                            uint8_t *dev_done, void *stream)
+{
+    return step_impl(h, dev_actions, action_dtype, K, dev_obs, dev_reward, dev_done, stream, h ? h->p.history : 1);
 }
 
 extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int32_t K, float *host_obs, float *host_reward,
@@ -473,13 +552,19 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     if (rc) return rc;
     if (K < 1 || !host_actions) return fail(SHIPSIM_ERR_ARG, "K must be >= 1 and host_actions non-NULL");
     DeviceGuard g(h->device);
-    const size_t n = (size_t)h->cfg.num_envs * K;
-    const size_t obs_f = n * kFrame * h->cfg.history;
+    const size_t N = (size_t)h->cfg.num_envs;
+    const size_t n = N * K;
+    // With HISTORY_SIZE = 2 an observation is [frame of the previous step | frame of this step] (ship_env.py:112-113):
+    // half of every row repeats the row before it.  Only the FRAMES cross PCIe (the kernel runs in its one-frame mode);
+    // the rows are put together on the host, chunk by chunk, while later chunks are still in flight.
+    const bool frames_only = h->cfg.history == 2 && host_obs != nullptr;
+    const int hist_dev = frames_only ? 1 : h->cfg.history;
+    const size_t obs_row = (size_t)kFrame * hist_dev;               // floats per device-side obs row
     if (K > h->stage_K) {
         cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
         h->d_act = nullptr; h->d_obs = nullptr; h->d_rew = nullptr; h->d_done = nullptr; h->stage_K = 0;
         CU(cudaMalloc(&h->d_act, n * sizeof(int32_t)));
-        CU(cudaMalloc(&h->d_obs, obs_f * sizeof(float)));
+        CU(cudaMalloc(&h->d_obs, n * kFrame * h->cfg.history * sizeof(float)));
         CU(cudaMalloc(&h->d_rew, n * sizeof(float)));
         CU(cudaMalloc(&h->d_done, n));
         h->stage_K = K;
@@ -488,28 +573,80 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     if (!h->copy_stream) {
         CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
         for (auto &ev : h->chunk_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        for (auto &ev : h->copy_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    uint8_t *done_dst = host_done;
+    if (frames_only) {
+        const size_t need = (n + N) * kFrame;                       // frame 0 = the state before the call
+        if (need > h->h_frames_cap) {
+            if (h->h_frames) cudaFreeHost(h->h_frames);
+            h->h_frames = nullptr; h->h_frames_cap = 0;
+            CU(cudaHostAlloc(&h->h_frames, need * sizeof(float), cudaHostAllocDefault));
+            h->h_frames_cap = need;
+        }
+        if (!host_done && h->cfg.auto_reset) {
+            if (n > h->h_done_cap) {
+                if (h->h_done) cudaFreeHost(h->h_done);
+                h->h_done = nullptr; h->h_done_cap = 0;
+                CU(cudaHostAlloc(&h->h_done, n, cudaHostAllocDefault));
+                h->h_done_cap = n;
+            }
+            done_dst = h->h_done;
+        }
+        if (!h->d_frame0) CU(cudaMalloc(&h->d_frame0, N * kFrame * sizeof(float)));
+        if (!h->pool) {
+            int nt = std::max(1, std::min(16, (int)std::thread::hardware_concurrency()));
+            if (const char *ev = std::getenv("SHIPSIM_HOST_THREADS")) nt = std::max(1, atoi(ev));
+            h->pool = new HostPool(nt - 1);
+        }
+        CU(launch_frame(h->p, h->d_frame0, s));
+        h->launches++;
     }
     CU(cudaMemcpyAsync(h->d_act, host_actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    // The rollout is cut into chunks of steps: while chunk i+1 is being computed on the caller's stream, the
-    // observations / rewards / dones of chunk i travel to the host on the copy stream (the D2H copy dominates:
-    // 133 B per env-step over PCIe against ~0.5 ns of kernel time).
-    const size_t N = (size_t)h->cfg.num_envs, obs_row = (size_t)kFrame * h->cfg.history;
-    const int n_chunks = K >= 8 ? 8 : 1;
-    int k0 = 0;
+    // The rollout is cut into chunks of steps: while chunk i+1 is being computed on the caller's stream, the results
+    // of chunk i travel to the host on the copy stream (the D2H copy dominates: 69 B per env-step over PCIe against
+    // ~0.2 ns of kernel time) and chunk i-1 is being assembled by the host threads.
+    int n_chunks = K >= 64 ? 16 : (K >= 8 ? 8 : 1);
+    if (const char *ev = std::getenv("SHIPSIM_HOST_CHUNKS")) n_chunks = std::max(1, std::min({atoi(ev), (int)shipsim_handle::kMaxChunks, (int)K}));
+    int kbeg[shipsim_handle::kMaxChunks + 1];
+    for (int c = 0; c <= n_chunks; ++c) kbeg[c] = (int)((int64_t)K * c / n_chunks);
     for (int c = 0; c < n_chunks; ++c) {
-        const int k1 = (int)((int64_t)K * (c + 1) / n_chunks);
-        const int kc = k1 - k0;
+        const int k0 = kbeg[c], kc = kbeg[c + 1] - kbeg[c];
         if (kc <= 0) continue;
         const size_t off = (size_t)k0 * N;
-        const int rc2 = shipsim_step(h, h->d_act + off, SHIPSIM_ACTION_I32, kc, h->d_obs + off * obs_row, h->d_rew + off, h->d_done + off, stream);
+        const int rc2 = step_impl(h, h->d_act + off, SHIPSIM_ACTION_I32, kc, h->d_obs + off * obs_row, h->d_rew + off, h->d_done + off,
+                                  stream, hist_dev);
         if (rc2) return rc2;
-        cudaEvent_t ev = h->chunk_done[c & 1];
-        CU(cudaEventRecord(ev, s));
-        CU(cudaStreamWaitEvent(h->copy_stream, ev, 0));
-        if (host_obs) CU(cudaMemcpyAsync(host_obs + off * obs_row, h->d_obs + off * obs_row, (size_t)kc * N * obs_row * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+        CU(cudaEventRecord(h->chunk_done[c], s));
+        CU(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+        if (frames_only) {
+            if (c == 0) CU(cudaMemcpyAsync(h->h_frames, h->d_frame0, N * kFrame * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+            CU(cudaMemcpyAsync(h->h_frames + (off + N) * kFrame, h->d_obs + off * obs_row, (size_t)kc * N * obs_row * sizeof(float),
+                               cudaMemcpyDeviceToHost, h->copy_stream));
+        } else if (host_obs) {
+            CU(cudaMemcpyAsync(host_obs + off * obs_row, h->d_obs + off * obs_row, (size_t)kc * N * obs_row * sizeof(float),
+                               cudaMemcpyDeviceToHost, h->copy_stream));
+        }
         if (host_reward) CU(cudaMemcpyAsync(host_reward + off, h->d_rew + off, (size_t)kc * N * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-        if (host_done) CU(cudaMemcpyAsync(host_done + off, h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, h->copy_stream));
-        k0 = k1;
+        if (done_dst) CU(cudaMemcpyAsync(done_dst + off, h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, h->copy_stream));
+        CU(cudaEventRecord(h->copy_done[c], h->copy_stream));
+    }
+    if (frames_only) {
+        // obs[k][e] = [frame k-1 | frame k]; a step that ended an episode under auto-reset returns the reset observation
+        // [-1 x 16 | reset frame] (ship_env.py:180-184), and its frame IS the reset frame
+        const float *fr = h->h_frames;
+        const bool cut = h->cfg.auto_reset != 0;
+        constexpr int kRowsPerJob = 2048;
+        for (int c = 0; c < n_chunks; ++c) {
+            if (kbeg[c + 1] <= kbeg[c]) continue;
+            CU(cudaEventSynchronize(h->copy_done[c]));
+            const size_t r0 = (size_t)kbeg[c] * N, r1 = (size_t)kbeg[c + 1] * N;
+            const int jobs = (int)((r1 - r0 + kRowsPerJob - 1) / kRowsPerJob);
+            h->pool->run(jobs, [&](int j) {
+                const size_t a = r0 + (size_t)j * kRowsPerJob, b = std::min(r1, a + kRowsPerJob);
+                assemble_history_rows(host_obs, fr, cut ? done_dst : nullptr, a, b, N);
+            });
+        }
     }
     CU(cudaStreamSynchronize(h->copy_stream));
     CU(cudaStreamSynchronize(s));

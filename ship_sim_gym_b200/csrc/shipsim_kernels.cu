@@ -581,6 +581,26 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
     }
 }
 
+// the observation frame of the CURRENT state of every env (ShipEnv.__add_states, ship_env.py:79-113): what the next
+// step will report as its "previous" frame.  Used by shipsim_step_host, which ships frames and rebuilds the history.
+__global__ void __launch_bounds__(256) frame_kernel(const __grid_constant__ StepParams p, float4 *out)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= p.N) return;
+    EnvRegs r;
+    float4 l0, l1, l2, g0, g1, g2;
+    load_env(p, e, r, l0, l1, l2, g0, g1, g2);
+    float2 g[kGoals];
+    unpack_goals(g0, g1, g2, g);
+    float gx, gy;
+    closest_goal(g, r.alive, r.x, r.y, gx, gy);
+    float4 *o = out + (size_t)e * 4;
+    o[0] = make_float4(r.x, r.y, (float)r.rudder, r.th);
+    o[1] = make_float4(gx, gy, l0.x, l0.y);
+    o[2] = make_float4(l0.z, l0.w, l1.x, l1.y);
+    o[3] = make_float4(l1.z, l1.w, l2.x, l2.y);
+}
+
 // stats slots -> out[kStatLen]; one warp per statistic column
 __global__ void stats_reduce_kernel(double *slots, double *out, int clear)
 {
@@ -637,6 +657,12 @@ cudaError_t launch_reset(const StepParams &p, const uint8_t *mask, const int *sc
 {
     const int threads = 256;
     reset_kernel<<<(p.N + threads - 1) / threads, threads, 0, stream>>>(p, mask, scenario, first, obs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frame(const StepParams &p, float4 *out, cudaStream_t stream)
+{
+    frame_kernel<<<(p.N + 255) / 256, 256, 0, stream>>>(p, out);
     return cudaGetLastError();
 }
 

@@ -326,10 +326,10 @@ class BatchedShipEnv(object):
         if out is None:
             out = (np.empty((K, self.num_envs, self._obs_dim_kernel), dtype=np.float32),
                    np.empty((K, self.num_envs), dtype=np.float32), np.empty((K, self.num_envs), dtype=np.uint8))
-        obs, rew, done = out
+        obs, rew, done = out           # any of them may be None: that output is then not copied back
+        ptr = lambda x: None if x is None else x.ctypes.data    # noqa: E731
         with torch.cuda.device(self.device):
-            _abi.check(self.L.shipsim_step_host(self._h, a.ctypes.data, K, obs.ctypes.data, rew.ctypes.data,
-                                                done.ctypes.data, self._stream()))
+            _abi.check(self.L.shipsim_step_host(self._h, a.ctypes.data, K, ptr(obs), ptr(rew), ptr(done), self._stream()))
         self.total_steps += K * self.num_envs
         return obs, rew, done
 

@@ -294,3 +294,33 @@ def test_many_candidate_planes_serial_path(lanes):
     assert rep["excluded_frac"] < 0.1, rep
     assert (ref["flags"] & oracle.FLAG_COLLIDING).any() and (orc.lidar[:, :10] >= 0).mean() > 0.1
     env.close()
+
+
+@pytest.mark.parametrize("auto_reset", [True, False])
+@pytest.mark.parametrize("n,K", [(1000, 100), (300, 7)])
+def test_host_path_rebuilds_history_from_frames(auto_reset, n, K):
+    """shipsim_step_host ships one frame per env-step and rebuilds [previous frame | frame] rows on the host
+    (reset observations included): bit-identical to the device-resident rollout, across consecutive calls, after a
+    state injection, and when the caller does not ask for the done flags."""
+    from ship_sim_gym_b200 import BatchedShipEnv, ScenarioBank
+    bank = ScenarioBank.generate(16, (600, 600), seed=2)
+    rng = np.random.RandomState(4)
+    envs = [BatchedShipEnv(n, bank=bank, seed=1, auto_reset=auto_reset) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    st = parity.f32_inputs(*parity.random_states(rng, n, 600, 600, 16, bank.goals))
+    for it in range(3):
+        if it == 1:
+            for e in envs:
+                e.set_state(*st)
+        acts = rng.randint(0, 3, (K, n)).astype(np.int32)
+        o, r, d = [t.cpu().numpy() for t in envs[0].rollout(torch.tensor(acts, device="cuda"))]
+        if it == 2:
+            ho = np.empty((K, n, 32), dtype=np.float32)
+            envs[1].step_host(acts, K=K, out=(ho, None, None))
+        else:
+            ho, hr, hd = envs[1].step_host(acts, K=K)
+            assert np.array_equal(hr, r) and np.array_equal(hd, d)
+        assert np.array_equal(ho, o), "call %d" % it
+        if auto_reset and K >= 100:
+            assert d.sum() > 0
