@@ -260,6 +260,7 @@ __device__ __forceinline__ bool goal_contact(const StepParams &p, float qx, floa
     return !goal_culled(p, qx, qy) && goal_touches_ship(p, qx, qy);
 }
 
+__device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
 // 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, completes in the background

@@ -495,16 +495,20 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
 #pragma unroll 1
             for (int elr = 0; elr < E; ++elr) {
                 const int4 ev = s_env[warp * E + elr];              // k0, committed, carry slot, reset
-                const int last = ev.w ? ev.y - 1 : -1;              // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
-                const float4 rfv = (half == 0 || q >= 2) ? neg : s_rf[(warp * E + elr) * 2 + q];
                 const float4 *fb = s_frame + wfr0 + elr * FR4 + q;
                 float4 *o = p.obs + ((size_t)(ev.x + r0) * p.N + (warp_env0 + elr)) * OBS4 + col;
                 int slot = ring(ev.z + r0 + half);
-                for (int tr = r0; tr < ev.y; tr += RPR) {
-                    __stcs(o, tr == last ? rfv : fb[slot * FS4]);
+                const int nplain = ev.w ? ev.y - 1 : ev.y;          // the last committed row of an env that resets is special
+#pragma unroll 2
+                for (int tr = r0; tr < nplain; tr += RPR) {
+                    __stcs(o, fb[slot * FS4]);
                     o += rstride * RPR;
                     slot += RPR;
                     if (slot >= NS) slot -= NS;
+                }
+                if (ev.w && r0 == 0) {                              // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
+                    const float4 rfv = (half == 0 || q >= 2) ? neg : s_rf[(warp * E + elr) * 2 + q];
+                    __stcs(p.obs + ((size_t)(ev.x + nplain) * p.N + (warp_env0 + elr)) * OBS4 + col, rfv);
                 }
             }
         }
@@ -536,6 +540,8 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
         }
         a_my = 3;
         if (valid && k0 + t < p.K) a_my = load_action(p, act0 + (size_t)(k0 + t) * act_stride, k0 + t, gid);
+        // the window after next starts somewhere in (k0, k0 + T]: pull its action rows into L2 now
+        if (p.action_dtype != 3 && valid && k0 + T + t < p.K) prefetch_l2(act0 + (size_t)(k0 + T + t) * act_stride);
         __syncwarp();
     }
 
