@@ -206,13 +206,12 @@ def main():
     gen = torch.Generator(device=dev).manual_seed(SEED + rank)
     actions = torch.randint(0, 3, (ROLLOUT, ENVS), dtype=torch.int32, device=dev, generator=gen)
     out = env.alloc_rollout(ROLLOUT)
-    stats = torch.zeros(16, dtype=torch.float64, device=dev)
+    reducer = sdist.StatsReducer(dev)
 
     def one_step():
         env.rollout(actions, out=out)
-        if world > 1:
-            stats.copy_(env.stats_tensor(clear=True))
-            sdist.all_reduce_stats(stats)
+        if world > 1:       # one all-reduce of the episode statistics per rollout; it overlaps the next rollout's kernel
+            reducer.submit(env.stats_tensor(clear=True))
 
     def barrier():
         if world > 1:
@@ -229,6 +228,7 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         one_step()
+    reducer.wait_all()                      # the last all-reduce belongs to the timed region
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)

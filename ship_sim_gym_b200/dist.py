@@ -42,6 +42,41 @@ def all_reduce_stats(stats):
     return stats
 
 
+class StatsReducer(object):
+    """The per-rollout statistics all-reduce, off the critical path: the reduction of rollout i runs on the
+    communication stream while the step kernel of rollout i+1 is already executing (the kernel does not depend on it).
+    Two buffers alternate; `submit` only makes the CURRENT STREAM wait for the all-reduce that last used the buffer it
+    is about to overwrite -- the host never blocks."""
+
+    def __init__(self, device, n=16):
+        self.bufs = [torch.zeros(n, dtype=torch.float64, device=device) for _ in range(2)]
+        self.work = [None, None]
+        self.i = 0
+        self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def submit(self, stats_vec):
+        """stats_vec: this rank's float64[16] vector (device).  Returns the buffer that will hold the global sums."""
+        k = self.i & 1
+        self.i += 1
+        if self.work[k] is not None:
+            self.work[k].wait()
+        self.bufs[k].copy_(stats_vec)
+        if self.on:
+            self.work[k] = dist.all_reduce(self.bufs[k], op=dist.ReduceOp.SUM, async_op=True)
+        return self.bufs[k]
+
+    def latest(self):
+        """Global sums of the most recently submitted rollout (the current stream waits for its all-reduce)."""
+        self.wait_all()
+        return self.bufs[(self.i - 1) & 1]
+
+    def wait_all(self):
+        for k in range(2):
+            if self.work[k] is not None:
+                self.work[k].wait()
+                self.work[k] = None
+
+
 def summarize(stats_vec, names):
     """Global means from the reduced vector (what Curriculum.progress is fed)."""
     v = [float(x) for x in stats_vec.tolist()]

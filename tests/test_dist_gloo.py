@@ -47,6 +47,11 @@ def _worker(rank, world, port, q):
     out, stats = _run_shard(off, cnt)
     t = torch.from_numpy(stats.copy())
     sdist.all_reduce_stats(t)
+    # the overlapped reducer (what bench.py uses): three submissions through two alternating buffers
+    red = sdist.StatsReducer("cpu")
+    for i in range(3):
+        red.submit(torch.from_numpy(stats * (i + 1)))
+    assert torch.allclose(red.latest(), t * 3)
     q.put((rank, off, cnt, out["reward"].sum(), out["done"].sum(), out["obs"][-1].copy(), t.numpy().copy()))
     dist.barrier()
     dist.destroy_process_group()
