@@ -19,8 +19,16 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"        # NCCL's version banner goes to stdout: rank 0 prints ONE JSON line
+
+# Rank 0 prints ONE JSON line on stdout.  Libraries write there too (NCCL's version banner), so file descriptor 1 is
+# pointed at stderr for the duration of the run and the line goes to the real stdout at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 ENVS = 4096          # BASELINE.json configs[1]
 ROLLOUT = 1000       # env-steps per launch ("1,000 steps")
@@ -159,7 +167,7 @@ def run_reference_arm(args, rank, world):
         "note": "reference = pure Python over pymunk/Chipmunk (not installable here); timed arm is the float64 C "
                 "restatement in oracle/ (faster than the real Python env: no cffi, no pygame, no clock.tick sleep)",
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(world):
@@ -211,7 +219,11 @@ def main():
     def one_step():
         env.rollout(actions, out=out)
         if world > 1:       # one all-reduce of the episode statistics per rollout; it overlaps the next rollout's kernel
-            reducer.submit(env.stats_tensor(clear=True))
+            mode = os.environ.get("SHIPSIM_BENCH_REDUCE", "full")
+            if mode == "full":
+                reducer.submit(env.stats_tensor(clear=True))
+            elif mode == "local":
+                env.stats_tensor(clear=True)
 
     def barrier():
         if world > 1:
@@ -310,7 +322,7 @@ def main():
             "launch_shape": {k: info[k] for k in ("lanes_per_env", "threads_per_cta", "ctas", "steps_in_flight")},
             "stats": env.stats(), "extra": extra,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -21,6 +21,9 @@ def init(backend=None):
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         kw = {}
         if backend == "nccl":
+            # The statistics all-reduce is a tiny kernel racing a step kernel that fills every SM: on a high-priority
+            # stream its one CTA is placed first instead of queueing behind the whole next rollout.
+            os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
             torch.cuda.set_device(local)
             kw["device_id"] = torch.device("cuda", local)
         dist.init_process_group(backend=backend, **kw)
