@@ -26,6 +26,11 @@ _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 
 
+if os.environ.get("SHIPSIM_BENCH_WATCHDOG"):        # debugging aid: dump every thread's stack if the run is still going after N seconds
+    import faulthandler
+    faulthandler.dump_traceback_later(float(os.environ["SHIPSIM_BENCH_WATCHDOG"]), exit=True)
+
+
 def emit(line):
     sys.stdout.flush()
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -247,8 +252,8 @@ def main():
     launches = env.launch_info()["launches"] - l0
     if sampler.nv is not None and len(sampler.samples) < 5:       # region too short for NVML: extend, untimed
         t_end = time.time() + 0.5
-        while time.time() < t_end:
-            one_step()
+        while time.time() < t_end:          # no collective in here: ranks run different numbers of these
+            env.rollout(actions, out=out)
         torch.cuda.synchronize()
     clocks = sampler.stop()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
