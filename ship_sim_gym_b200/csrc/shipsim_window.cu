@@ -8,14 +8,18 @@
 // query, the ship-vs-bank overlap test, the goal tests, the observation frame -- is a pure function of one pose and
 // feeds back into the trajectory only through `done` (auto-reset).  So, when the actions of the rollout are known up
 // front (they are: shipsim_step takes the whole [K][N] action tensor), T consecutive steps of one env are SPECULATED:
-//   1. every lane of the env's group runs the T-step physics recurrence (redundantly, in lockstep, no traffic) and
-//      keeps the pose of "its" step t = lane % T;
+//   1. the sequential part runs as two short scans executed by every lane of the env's group in lockstep (no
+//      divergence, no waiting): rudder / angular velocity / angle from pre-decoded actions, then ONE sincos per lane,
+//      then velocity / position with the thrust terms broadcast by shuffles; the group's first lane drops each step's
+//      result into shared memory and lane t = lane % T picks up the pose of "its" step;
 //   2. lane t does the pose-dependent work of step t -- reach-grid lookup, plane phase, goal tests, out-of-bounds --
 //      and the cooperative ray / separating-axis passes run over (env, step) pairs instead of envs;
-//   3. the sequential leftovers are resolved with short scans: goals taken (prefix OR), episode return (ordered sum,
-//      same rounding as the serial kernel), sticky lidar readings (models.py:71: a miss keeps the last hit);
+//   3. the sequential leftovers are resolved without loops over steps where possible: goals taken (one ballot per
+//      goal), episode return (ordered per-lane prefix, same rounding as the serial kernel), sticky lidar readings
+//      (models.py:71: a miss keeps the last hit -- per ray, the latest hitting lane at or before t, by ballot + clz);
 //   4. the window is cut after the first `done`: steps beyond it are discarded, the env resets and the next window
-//      starts from the reset state (episodes last ~50 steps, so a window of 8 wastes ~7 % of its lanes).
+//      starts from the reset state (episodes last ~48 steps on the default map, so a window of 16 commits 13.9 steps
+//      on average).
 // A warp holds E = 32/T envs; envs of a warp advance independently (each has its own step cursor k0).
 //
 // Shared-memory rings (per env, T+1 slots): observation frames and plane-phase rows.  Slot cb is the "carry": the
