@@ -127,11 +127,17 @@ __device__ __forceinline__ int random_action(const StepParams &p, long long gid,
 // Cody-Waite reduction by pi/2 (3 constants, exact for |x| < ~1e5, which bounds any reachable angle:
 // |w| <= ~1.4 rad/s * dt over at most max_steps steps) + the usual minimax polynomials on [-pi/4, pi/4];
 // ~1 ulp, no local-memory slow path in the hot loop (libdevice's Payne-Hanek branch is kept for huge angles).
-static __device__ __noinline__ void sincos_huge(float x, float *sn, float *cs) { sincosf(x, sn, cs); }   // never in practice: keep it out of the loop body
+// never taken in practice: kept out of the loop body (returns by value -- pointers would pin sin / cos to local memory)
+static __device__ __noinline__ float2 sincos_huge(float x)
+{
+    float sn, cs;
+    sincosf(x, &sn, &cs);
+    return make_float2(sn, cs);
+}
 
 __device__ __forceinline__ void sincos_fast(float x, float &sn, float &cs)
 {
-    if (fabsf(x) > 1.0e5f) { sincos_huge(x, &sn, &cs); return; }
+    if (fabsf(x) > 1.0e5f) { const float2 v = sincos_huge(x); sn = v.x; cs = v.y; return; }
     const float q = rintf(x * 0.636619772367581343f);          // 2/pi
     float r = fmaf(q, -1.57079601287841796875f, x);
     r = fmaf(q, -3.1391647326017846353352069854736e-07f, r);
