@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
         s_ray[32 + threadIdx.x] = p.ray_s[threadIdx.x % kBeams];
     }
     if (lane < 8) stat[lane] = 0.f;
+    if (!valid && gl == 0) s_scr[my0] = make_float4(1.f, 0.f, 0.f, 0.f);      // idle groups: a defined heading for the shadow lanes
     const int lps_sh = p.hull_max <= 8 ? 3 : (p.hull_max <= 16 ? 4 : 5);    // SAT pass: log2(lanes per env slot)
     const int lps = 1 << lps_sh, nslots = 32 >> lps_sh;
     const int sslot = lane >> lps_sh, sel = lane & (lps - 1);
@@ -96,7 +97,6 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
     sincos_fast(r.th, s, c);
     hull_half_extents(p, c, s, hx, hy);
     uint4 cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
-    float cpre = c, spre = s;                    // trig of the pose the current step starts from (thrust direction)
     bool goals_dirty = false;
     const size_t act_esize = p.action_dtype == 1 ? 8 : (p.action_dtype == 2 ? 1 : 4);
     const size_t act_stride = (size_t)p.N * act_esize;
@@ -133,7 +133,10 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
             if (HIST == 2 && gl == 0) { row4[0] = row4[4]; row4[1] = row4[5]; row4[2] = row4[6]; row4[3] = row4[7]; }
 
             // ---- ShipGame.handle_discrete_action (game.py:140-153); Ship.move_forward / rotate (models.py:129-146)
-            if (a == 0) { dvx = -p.acc_dt * spre; dvy = p.acc_dt * cpre; dw = -p.ang_dt * (float)r.rudder; }
+            if (a == 0) {                       // thrust along the heading the step starts from: its trig is in the row header
+                const float4 h0 = myscr[0];
+                dvx = -p.acc_dt * h0.y; dvy = p.acc_dt * h0.x; dw = -p.ang_dt * (float)r.rudder;
+            }
             else if (a == 1) r.rudder = max(r.rudder - 5, -10);
             else if (a == 2) r.rudder = min(r.rudder + 5, 10);
 
@@ -286,6 +289,14 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                     const float4 *rec = p.bank + (size_t)(bsa & 0x0fffffffu) * p.scen_stride4;
                     const float4 hdr = __ldg(rec + 4);
                     const float4 *bE = rec + kBankHeader4;
+                    // the edge records of both banks are requested together with the header: their addresses do not
+                    // depend on it (every slot below maxv exists), so one memory round trip serves the whole pass
+                    float4 edb[2];
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        edb[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (act_env && ((bsa >> (28 + b)) & 1u) && sel < p.maxv) edb[b] = __ldg(bE + b * p.maxv + sel);
+                    }
                     float rx[kShipVerts], ry[kShipVerts];
 #pragma unroll
                     for (int j = 0; j < kShipVerts; ++j) {
@@ -298,8 +309,7 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                         const bool do_b = act_env && ((bsa >> (28 + b)) & 1u) && !coll;
                         const int nb = __float_as_int(b ? hdr.w : hdr.z);
                         const bool actl = do_b && sel < nb;
-                        float4 ed = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (actl) ed = __ldg(bE + b * p.maxv + sel);
+                        const float4 ed = edb[b];
                         const unsigned sb = __ballot_sync(kFull, actl && bank_axis_separates(ed, rx, ry, bx, by));   // a bank edge normal separates
                         bool sep = (sb & slotmask) != 0u;
                         if (__ballot_sync(kFull, do_b && !sep)) {                           // else try the ship's edge normals
@@ -376,7 +386,6 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
         // so that the grid cell of the new pose is requested as early as possible: it is consumed an iteration later.
         const float fx = r.x, fy = r.y, fth = r.th;                 // this step's pose, for the observation frame
         if (k + 1 < p.K) {
-            cpre = c; spre = s;
             r.x += r.vx * p.dt;
             r.y += r.vy * p.dt;
             r.th += r.w * p.dt;
