@@ -230,6 +230,11 @@ static int derive_params(shipsim_handle *h)
     const double delta = ((double)c.lidar_spread_deg / c.lidar_beams) * deg;
     const double start = (90.0 - (double)c.lidar_spread_deg / 2.0) * deg;
     for (int i = 0; i < kBeams; ++i) { p.ray_c[i] = (float)std::cos(start + delta * i); p.ray_s[i] = (float)std::sin(start + delta * i); }
+    {
+        const double mid = start + delta * (kBeams - 1) * 0.5, half = std::fabs(delta) * (kBeams - 1) * 0.5;
+        p.fan_cx = (float)std::cos(mid); p.fan_cy = (float)std::sin(mid);
+        p.fan_cos = (float)std::cos(half); p.fan_sin = (float)std::sin(half);
+    }
     // reach grid: kGridN x kGridN cells over the bounds plus a pad (the ray origin of a live env lies within
     // [0, W + ship extent]); the border cells are unbounded
     const double pad = 32.0;

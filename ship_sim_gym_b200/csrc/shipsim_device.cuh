@@ -82,6 +82,7 @@ struct StepParams {
     float ang_dt;                // thrust/moment*dt      (w += t*i_inv*dt, t = -rudder*thrust)
     float goal_r, step_penalty, spawn_x, spawn_y;
     float ray_c[kBeams], ray_s[kBeams];              // cos/sin of radians(90 - spread/2 + i*spread/n) (models.py:48-49,62)
+    float fan_cx, fan_cy, fan_cos, fan_sin;          // body-frame axis of the ray fan, cos/sin of its half opening
     float ship_lx[kShipVerts], ship_ly[kShipVerts];  // body-frame hull, CCW (models.py:6,88 through cpConvexHull)
     float ship_nx[kShipVerts], ship_ny[kShipVerts];  // body-frame outward normal of edge j-1 -> j
     float ship_off[kShipVerts];                      // ship_n[j] . ship_l[j]: offset of the hull's plane j (rotation invariant)

@@ -128,6 +128,7 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
     const EdgeD *E = p.edges_d + (size_t)scen * (2 * kMaxHull);
     const double xd = (double)x, yd = (double)y, hxd = (double)hx, hyd = (double)hy;
     unsigned outm = 0u, sepm = 0u;
+    int nk = 0;                                  // planes kept for the ray pass
 #pragma unroll 1
     for (int n = 0; n < ncand; ++n) {
         double2 nd;
@@ -145,21 +146,31 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
         const unsigned bbit = bank1 ? 2u : 1u;
         const PlaneEval pe = eval_plane_rec(nd, ev, xd, yd, hxd, hyd);
         if (pe.d > 0.f) outm |= bbit;
+        // the normal in the body frame, where both the hull and the ray fan are constant
+        const float bnx = pe.nx * c + pe.ny * s, bny = pe.ny * c - pe.nx * s;
         if (WITH_SAT) {
-            // does this bank plane have the whole ship in front of it?  n.(hull vertex j - v_i) = d - n.h + (R^T n).l_j:
-            // the normal is rotated into the body frame, where the hull is constant (vertex 0 is the body origin)
-            const float bnx = pe.nx * c + pe.ny * s, bny = pe.ny * c - pe.nx * s;
+            // does this bank plane have the whole ship in front of it?  n.(hull vertex j - v_i) = d - n.h + (R^T n).l_j
+            // (vertex 0 is the body origin)
             float m = 0.f;
 #pragma unroll
             for (int j = 1; j < kShipVerts; ++j) m = fminf(m, bnx * p.ship_lx[j] + bny * p.ship_ly[j]);
             if (pe.d - (pe.nx * hx + pe.ny * hy) + m > 0.f) sepm |= bbit;
         }
-        row[1 + 2 * n] = make_float4(pe.d, pe.ta, -L * pe.nx, -L * pe.ny);
-        row[2 + 2 * n] = make_float4(pe.len, bank1 ? 1.f : 0.f, 0.f, 0.f);
+        // Can any ray of the fan reach this plane at all?  A ray hits only if 0 <= d <= -L n.dir (ray_vs_plane), and over
+        // the fan -n.dir <= cos(max(0, angle(-n, fan axis) - half spread)).  Planes that fail (with a margin far above
+        // fp32 rounding) are left out of the row: fewer planes per ray, and often no ray pass for the env at all.
+        const float cm = -(bnx * p.fan_cx + bny * p.fan_cy);
+        float reach = 1.f;
+        if (cm < p.fan_cos) reach = cm * p.fan_cos + sqrtf(fmaxf(1.f - cm * cm, 0.f)) * p.fan_sin;
+        if (pe.d >= 0.f && pe.d <= L * reach * 1.0001f + 1.0e-3f) {
+            row[1 + 2 * nk] = make_float4(pe.d, pe.ta, -L * pe.nx, -L * pe.ny);
+            row[2 + 2 * nk] = make_float4(pe.len, bank1 ? 1.f : 0.f, 0.f, 0.f);
+            ++nk;
+        }
     }
     // cpShapeSegmentQuery: start point inside the shape => alpha = 0 and `point` stays at the ray end
     const unsigned inm = cell.z & 3u & ~outm;
-    row[0] = make_float4(c, s, __int_as_float(ncand | (int)(inm << 8)), 0.f);
+    row[0] = make_float4(c, s, __int_as_float(nk | (int)(inm << 8)), 0.f);
     return near & ~sepm;
 }
 
