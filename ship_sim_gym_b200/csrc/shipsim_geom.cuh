@@ -161,7 +161,7 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
         // fp32 rounding) are left out of the row: fewer planes per ray, and often no ray pass for the env at all.
         const float cm = -(bnx * p.fan_cx + bny * p.fan_cy);
         float reach = 1.f;
-        if (cm < p.fan_cos) reach = cm * p.fan_cos + sqrtf(fmaxf(1.f - cm * cm, 0.f)) * p.fan_sin;
+        if (cm < p.fan_cos) reach = cm * p.fan_cos + sqrt_approx(fmaxf(1.f - cm * cm, 0.f)) * p.fan_sin;    // a bound: approx is plenty
         if (pe.d >= 0.f && pe.d <= L * reach * 1.0001f + 1.0e-3f) {
             row[1 + 2 * nk] = make_float4(pe.d, pe.ta, -L * pe.nx, -L * pe.ny);
             row[2 + 2 * nk] = make_float4(pe.len, bank1 ? 1.f : 0.f, 0.f, 0.f);

@@ -344,16 +344,9 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
             const bool timeout = (r.steps >= p.max_steps);
             done = colliding || all_goals || oob || timeout;             // ship_env.py:115-134
 
-            if (leader && goal_reached) atomicAdd(stat + 3, 1.f);
+            warp_stats(stat, lane, leader, goal_reached, done, colliding, oob, timeout, all_goals, r.ret, r.steps);
             do_reset = done && p.auto_reset;
             if (done) {
-                if (leader) {                                           // episode statistics, per-warp accumulators
-                    atomicAdd(stat + 0, 1.f); atomicAdd(stat + 1, r.ret); atomicAdd(stat + 2, (float)r.steps);
-                    if (colliding) atomicAdd(stat + 4, 1.f);
-                    if (oob) atomicAdd(stat + 5, 1.f);
-                    if (timeout) atomicAdd(stat + 6, 1.f);
-                    if (all_goals) atomicAdd(stat + 7, 1.f);
-                }
                 if (do_reset) {
                     const int ep = r.episode + 1;
                     reset_env(p, r, pick_scenario(p, p.env_id_offset + e, ep), ep);

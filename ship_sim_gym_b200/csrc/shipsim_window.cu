@@ -409,16 +409,7 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
             const float rv = __shfl_sync(kFull, reward, gbase + i);
             if (i <= t) my_ret += rv;
         }
-        if (commit) {
-            if (goal_reached) atomicAdd(stat + 3, 1.f);
-            if (done) {
-                atomicAdd(stat + 0, 1.f); atomicAdd(stat + 1, my_ret); atomicAdd(stat + 2, (float)steps_t);
-                if (colliding) atomicAdd(stat + 4, 1.f);
-                if (oob) atomicAdd(stat + 5, 1.f);
-                if (timeout) atomicAdd(stat + 6, 1.f);
-                if (all_goals) atomicAdd(stat + 7, 1.f);
-            }
-        }
+        warp_stats(stat, lane, commit, goal_reached, done, colliding, oob, timeout, all_goals, my_ret, steps_t);
         // this step's frame: pose, rudder, nearest remaining goal (closest_goal, game.py:333-349), and the lidar
         // readings.  Sticky readings (models.py:71): a ray that missed keeps the reading of the last step at which it
         // hit -- the latest hit at or before step t inside the window (found with a ballot per ray), else the carry's.
