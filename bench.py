@@ -226,7 +226,8 @@ def main():
         if world > 1:       # one all-reduce of the episode statistics per rollout; it overlaps the next rollout's kernel
             mode = os.environ.get("SHIPSIM_BENCH_REDUCE", "full")
             if mode == "full":
-                reducer.submit(env.stats_tensor(clear=True))
+                env.stats_tensor(clear=True, out=reducer.next_buffer())
+                reducer.reduce()
             elif mode == "local":
                 env.stats_tensor(clear=True)
 

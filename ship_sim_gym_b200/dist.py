@@ -48,33 +48,44 @@ def all_reduce_stats(stats):
 class StatsReducer(object):
     """The per-rollout statistics all-reduce, off the critical path: the reduction of rollout i runs on the
     communication stream while the step kernel of rollout i+1 is already executing (the kernel does not depend on it).
-    Two buffers alternate; `submit` only makes the CURRENT STREAM wait for the all-reduce that last used the buffer it
-    is about to overwrite -- the host never blocks."""
+    `depth` buffers rotate; `next_buffer` only makes the CURRENT STREAM wait for the all-reduce that last used the
+    buffer about to be overwritten -- the host never blocks, and ranks may drift up to depth - 1 rollouts apart, so a
+    rank that happens to draw a slow rollout does not stall the others."""
 
-    def __init__(self, device, n=16):
-        self.bufs = [torch.zeros(n, dtype=torch.float64, device=device) for _ in range(2)]
-        self.work = [None, None]
+    def __init__(self, device, n=16, depth=4):
+        self.bufs = [torch.zeros(n, dtype=torch.float64, device=device) for _ in range(depth)]
+        self.work = [None] * depth
         self.i = 0
         self.on = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
-    def submit(self, stats_vec):
-        """stats_vec: this rank's float64[16] vector (device).  Returns the buffer that will hold the global sums."""
-        k = self.i & 1
-        self.i += 1
+    def next_buffer(self):
+        """The buffer the next rollout's local statistics go into (e.g. BatchedShipEnv.stats_tensor(out=...))."""
+        k = self.i % len(self.bufs)
         if self.work[k] is not None:
             self.work[k].wait()
-        self.bufs[k].copy_(stats_vec)
+            self.work[k] = None
+        return self.bufs[k]
+
+    def reduce(self):
+        """Start the all-reduce of the buffer handed out by the last next_buffer(); returns that buffer."""
+        k = self.i % len(self.bufs)
+        self.i += 1
         if self.on:
             self.work[k] = dist.all_reduce(self.bufs[k], op=dist.ReduceOp.SUM, async_op=True)
         return self.bufs[k]
 
+    def submit(self, stats_vec):
+        """Copy this rank's float64[16] vector into the next buffer and start its all-reduce."""
+        self.next_buffer().copy_(stats_vec)
+        return self.reduce()
+
     def latest(self):
         """Global sums of the most recently submitted rollout (the current stream waits for its all-reduce)."""
         self.wait_all()
-        return self.bufs[(self.i - 1) & 1]
+        return self.bufs[(self.i - 1) % len(self.bufs)]
 
     def wait_all(self):
-        for k in range(2):
+        for k in range(len(self.bufs)):
             if self.work[k] is not None:
                 self.work[k].wait()
                 self.work[k] = None

@@ -334,11 +334,14 @@ class BatchedShipEnv(object):
         return obs, rew, done
 
     # ------------------------------------------------------------------------------------------ stats / state
-    def stats_tensor(self, clear=False):
-        """float64[16] device tensor (see shipsim_stat); ready to be all-reduced."""
+    def stats_tensor(self, clear=False, out=None):
+        """float64[16] device tensor (see shipsim_stat); ready to be all-reduced.  `out`: write into this tensor
+        (e.g. StatsReducer.next_buffer()) instead of the env's own."""
+        dst = self._stats_out if out is None else out
+        assert dst.dtype == torch.float64 and dst.numel() >= _abi.STATS_LEN and dst.is_contiguous()
         with torch.cuda.device(self.device):
-            _abi.check(self.L.shipsim_stats_read(self._h, self._stats_out.data_ptr(), int(clear), self._stream()))
-        return self._stats_out
+            _abi.check(self.L.shipsim_stats_read(self._h, dst.data_ptr(), int(clear), self._stream()))
+        return dst
 
     def stats(self, clear=False):
         v = self.stats_tensor(clear).cpu().tolist()
