@@ -174,6 +174,13 @@ int shipsim_step(shipsim_t *h, const void *dev_actions, int action_dtype, int32_
 int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int32_t K, float *host_obs, float *host_reward,
                       uint8_t *host_done, void *stream);
 
+/* The host half of shipsim_step_host, exposed for callers that move frames themselves (and for the CPU tests): build
+ * HISTORY_SIZE = 2 observation rows (ship_env.py:112-113) from frames.  host_frames holds the frame of the state before
+ * the first step for every env (num_envs x 16 floats) followed by one 16-float frame per row, rows ordered [step][env];
+ * host_obs[row] = [host_frames[row] | host_frames[row + num_envs]], except that where host_cut[row] != 0 (may be NULL)
+ * the first half is 16 x -1: the observation ShipEnv.reset returns (ship_env.py:180-184).  Pure host code, no device. */
+int shipsim_assemble_history(float *host_obs, const float *host_frames, const uint8_t *host_cut, int64_t n_rows, int64_t num_envs);
+
 /* Reduce the per-CTA statistic slots into dev_out[SHIPSIM_STATS_LEN] doubles (device memory, e.g. the tensor
  * handed to ncclAllReduce); clear != 0 zeroes the slots afterwards.  Replaces the counters ShipEnv keeps on the
  * Python object (ship_env.py:150,152,177). */

@@ -658,6 +658,13 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     return SHIPSIM_OK;
 }
 
+extern "C" int shipsim_assemble_history(float *host_obs, const float *host_frames, const uint8_t *host_cut, int64_t n_rows, int64_t num_envs)
+{
+    if (!host_obs || !host_frames || n_rows < 0 || num_envs < 1) return fail(SHIPSIM_ERR_ARG, "NULL buffer or bad sizes");
+    assemble_history_rows(host_obs, host_frames, host_cut, 0, (size_t)n_rows, (size_t)num_envs);
+    return SHIPSIM_OK;
+}
+
 extern "C" int shipsim_stats_read(shipsim_t *h, double *dev_out, int clear, void *stream)
 {
     const int rc = ready(h);

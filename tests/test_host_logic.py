@@ -114,3 +114,36 @@ def test_curriculum_driver_schedules_max_steps_and_bank_tiers():
     assert adv and mean == pytest.approx(0.5) and env2.loaded == ["easy", "hard"]
     with pytest.raises(ValueError):
         curriculum.CurriculumDriver(env2, cur, knob="bank")
+
+
+@pytest.mark.parametrize("align", [0, 4])
+def test_history_rows_from_frames_host_code(align):
+    """shipsim_assemble_history (the host half of shipsim_step_host, plain C++ with streaming stores): observation rows
+    [previous frame | frame] rebuilt from frames, reset rows included, for aligned (AVX-512 / SSE2 paths) and
+    unaligned (memcpy path) buffers.  No device involved."""
+    from ship_sim_gym_b200 import _abi
+    L = _abi.load()
+    rng = np.random.RandomState(0)
+    N, K = 37, 53
+    frames = rng.randn((K + 1) * N * 16).astype(np.float32)
+    cut = (rng.rand(K * N) < 0.1).astype(np.uint8)
+    want = np.empty((K * N, 32), dtype=np.float32)
+    f = frames.reshape(K + 1, N, 16)
+    want[:, :16] = f[:-1].reshape(-1, 16)
+    want[:, 16:] = f[1:].reshape(-1, 16)
+    want[cut != 0, :16] = -1.0
+    raw = np.zeros(K * N * 32 + 32, dtype=np.float32)
+    base = raw.ctypes.data
+    off = ((-base) % 64) // 4 + align // 4            # 64-byte aligned start, optionally knocked off by `align` bytes
+    out = raw[off:off + K * N * 32]
+    fr_raw = np.zeros(frames.size + 32, dtype=np.float32)
+    foff = ((-fr_raw.ctypes.data) % 64) // 4
+    fr = fr_raw[foff:foff + frames.size]
+    fr[:] = frames
+    _abi.check(L.shipsim_assemble_history(out.ctypes.data, fr.ctypes.data, cut.ctypes.data, K * N, N))
+    assert np.array_equal(out.reshape(-1, 32), want)
+    _abi.check(L.shipsim_assemble_history(out.ctypes.data, fr.ctypes.data, None, K * N, N))     # no cut: plain history
+    want[:, :16] = f[:-1].reshape(-1, 16)
+    assert np.array_equal(out.reshape(-1, 32), want)
+    with pytest.raises(ValueError):
+        _abi.check(L.shipsim_assemble_history(None, fr.ctypes.data, None, 1, N))
