@@ -153,3 +153,25 @@ def test_auto_selection():
     assert e2.launch_info()["steps_in_flight"] == 1
     with pytest.raises(ValueError):
         _env(16, bank, steps_in_flight=5)
+
+
+def test_million_envs_agree_with_small_shards():
+    """BASELINE configs[3] size (1,048,576 envs, serial-in-time kernel, one lane per env) against 4,096-env shards of
+    the same global env ids run through the window kernel: results depend neither on the batch size nor on which
+    kernel computed them."""
+    from ship_sim_gym_b200 import BatchedShipEnv, ScenarioBank
+    n, K, m = 1048576, 32, 4096
+    bank = ScenarioBank.generate(256, (600, 600), seed=3)
+    big = BatchedShipEnv(n, bank=bank, seed=9, validate_actions=False)
+    big.reset()
+    obs, rew, done = big.rollout(None, K=K)                    # in-kernel Philox actions, keyed by global env id and step
+    assert big.launch_info()["steps_in_flight"] == 1 and big.launch_info()["lanes_per_env"] == 1
+    for off in (0, 517 * 1024, n - m):
+        small = BatchedShipEnv(m, bank=bank, seed=9, env_id_offset=off, validate_actions=False)
+        small.reset()
+        o, r, d = small.rollout(None, K=K)
+        assert small.launch_info()["steps_in_flight"] == 16
+        assert torch.equal(o, obs[:, off:off + m]) and torch.equal(r, rew[:, off:off + m]) and torch.equal(d, done[:, off:off + m])
+        small.close()
+    s = big.stats()
+    assert s["episodes"] == float(done.sum()) and s["episodes"] > 100000
