@@ -296,11 +296,11 @@ def main():
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    h2d_b, d2h_b = env.host_traffic()
     e2e = {"value": float(ENVS) * ROLLOUT * e2e_steps * world / float(t.item()), "unit": UNIT,
-           "h2d_bytes_per_step": int(h_act.numel() * 4),
-           # HISTORY_SIZE = 2: only the frames cross PCIe (64 B per env-step + the frame of the state before the call);
-           # shipsim_step_host rebuilds the 128-byte [previous | current] rows in the caller's buffer with host threads
-           "d2h_bytes_per_step": int(h_obs.numel() * 2 + ENVS * 64 + h_rew.numel() * 4 + h_done.numel()),
+           # counted by shipsim_step_host from the copies it issues.  HISTORY_SIZE = 2: only frames cross PCIe (64 B per
+           # env-step) and the 128-byte [previous | current] rows are rebuilt in the caller's buffer by host threads
+           "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
            "host_obs_bytes_per_step": int(h_obs.numel() * 4),
            "steps": e2e_steps, "api": "BatchedShipEnv.step_host -> shipsim_step_host (pinned host buffers)"}
 

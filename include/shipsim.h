@@ -203,6 +203,8 @@ int shipsim_render(shipsim_t *h, int32_t env_index, int32_t width, int32_t heigh
 /* Introspection for benchmarks: launches issued so far, lanes per env and CTA size actually used. */
 int shipsim_launch_count(const shipsim_t *h, int64_t *out);
 int shipsim_launch_shape(const shipsim_t *h, int32_t *lanes_per_env, int32_t *threads_per_cta, int32_t *ctas);
+/* bytes the last shipsim_step_host moved over PCIe (host->device actions; device->host frames / rows, rewards, dones) */
+int shipsim_host_traffic(const shipsim_t *h, int64_t *h2d_bytes, int64_t *d2h_bytes);
 /* steps of one env the last launch speculated together (1 = the serial-in-time kernel ran) */
 int shipsim_launch_window(const shipsim_t *h, int32_t *steps_in_flight);
 

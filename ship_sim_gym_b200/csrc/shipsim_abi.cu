@@ -98,6 +98,7 @@ struct shipsim_handle {
     size_t h_frames_cap = 0, h_done_cap = 0;
     float4 *d_frame0 = nullptr;
     HostPool *pool = nullptr;
+    int64_t last_h2d = 0, last_d2h = 0;      // bytes the last shipsim_step_host moved over PCIe
     int64_t launches = 0;
     LaunchShape shape{1, kThreads, 0, 1};
 };
@@ -563,8 +564,6 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     // half of every row repeats the row before it.  Only the FRAMES cross PCIe (the kernel runs in its one-frame mode);
     // the rows are put together on the host, chunk by chunk, while later chunks are still in flight.
     const bool frames_only = h->cfg.history == 2 && host_obs != nullptr;
-    const int hist_dev = frames_only ? 1 : h->cfg.history;
-    const size_t obs_row = (size_t)kFrame * hist_dev;               // floats per device-side obs row
     if (K > h->stage_K) {
         cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
         h->d_act = nullptr; h->d_obs = nullptr; h->d_rew = nullptr; h->d_done = nullptr; h->stage_K = 0;
@@ -608,6 +607,8 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
         h->launches++;
     }
     CU(cudaMemcpyAsync(h->d_act, host_actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    h->last_h2d = (int64_t)(n * sizeof(int32_t));
+    h->last_d2h = 0;
     // The rollout is cut into chunks of steps: while chunk i+1 is being computed on the caller's stream, the results
     // of chunk i travel to the host on the copy stream (the D2H copy dominates: 69 B per env-step over PCIe against
     // ~0.2 ns of kernel time) and chunk i-1 is being assembled by the host threads.
@@ -615,22 +616,30 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     if (const char *ev = std::getenv("SHIPSIM_HOST_CHUNKS")) n_chunks = std::max(1, std::min({atoi(ev), (int)shipsim_handle::kMaxChunks, (int)K}));
     int kbeg[shipsim_handle::kMaxChunks + 1];
     for (int c = 0; c <= n_chunks; ++c) kbeg[c] = (int)((int64_t)K * c / n_chunks);
+    const size_t row_full = (size_t)kFrame * h->cfg.history;        // floats per complete row; chunk regions of d_obs are sized for it
     for (int c = 0; c < n_chunks; ++c) {
         const int k0 = kbeg[c], kc = kbeg[c + 1] - kbeg[c];
         if (kc <= 0) continue;
         const size_t off = (size_t)k0 * N;
-        const int rc2 = step_impl(h, h->d_act + off, SHIPSIM_ACTION_I32, kc, h->d_obs + off * obs_row, h->d_rew + off, h->d_done + off,
-                                  stream, hist_dev);
+        const int hist_c = frames_only ? 1 : h->cfg.history;
+        float *d_chunk = h->d_obs + off * row_full;
+        const int rc2 = step_impl(h, h->d_act + off, SHIPSIM_ACTION_I32, kc, d_chunk, h->d_rew + off, h->d_done + off, stream, hist_c);
         if (rc2) return rc2;
         CU(cudaEventRecord(h->chunk_done[c], s));
         CU(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+        if (frames_only && c == 0) {
+            CU(cudaMemcpyAsync(h->h_frames, h->d_frame0, N * kFrame * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+            h->last_d2h += (int64_t)(N * kFrame * sizeof(float));
+        }
+        h->last_d2h += (int64_t)kc * N * ((host_reward ? 4 : 0) + (done_dst ? 1 : 0));
         if (frames_only) {
-            if (c == 0) CU(cudaMemcpyAsync(h->h_frames, h->d_frame0, N * kFrame * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-            CU(cudaMemcpyAsync(h->h_frames + (off + N) * kFrame, h->d_obs + off * obs_row, (size_t)kc * N * obs_row * sizeof(float),
-                               cudaMemcpyDeviceToHost, h->copy_stream));
+            h->last_d2h += (int64_t)kc * N * kFrame * sizeof(float);
+            CU(cudaMemcpyAsync(h->h_frames + (off + N) * kFrame, d_chunk, (size_t)kc * N * kFrame * sizeof(float), cudaMemcpyDeviceToHost,
+                               h->copy_stream));
         } else if (host_obs) {
-            CU(cudaMemcpyAsync(host_obs + off * obs_row, h->d_obs + off * obs_row, (size_t)kc * N * obs_row * sizeof(float),
-                               cudaMemcpyDeviceToHost, h->copy_stream));
+            h->last_d2h += (int64_t)kc * N * row_full * sizeof(float);
+            CU(cudaMemcpyAsync(host_obs + off * row_full, d_chunk, (size_t)kc * N * row_full * sizeof(float), cudaMemcpyDeviceToHost,
+                               h->copy_stream));
         }
         if (host_reward) CU(cudaMemcpyAsync(host_reward + off, h->d_rew + off, (size_t)kc * N * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
         if (done_dst) CU(cudaMemcpyAsync(done_dst + off, h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, h->copy_stream));
@@ -655,6 +664,14 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     }
     CU(cudaStreamSynchronize(h->copy_stream));
     CU(cudaStreamSynchronize(s));
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_host_traffic(const shipsim_t *h, int64_t *h2d_bytes, int64_t *d2h_bytes)
+{
+    if (!h) return fail(SHIPSIM_ERR_ARG, "NULL argument");
+    if (h2d_bytes) *h2d_bytes = h->last_h2d;
+    if (d2h_bytes) *d2h_bytes = h->last_d2h;
     return SHIPSIM_OK;
 }
 

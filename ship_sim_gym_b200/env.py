@@ -333,6 +333,12 @@ class BatchedShipEnv(object):
         self.total_steps += K * self.num_envs
         return obs, rew, done
 
+    def host_traffic(self):
+        """(host->device, device->host) bytes the last step_host() moved over PCIe."""
+        a, b = C.c_int64(), C.c_int64()
+        _abi.check(self.L.shipsim_host_traffic(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     # ------------------------------------------------------------------------------------------ stats / state
     def stats_tensor(self, clear=False, out=None):
         """float64[16] device tensor (see shipsim_stat); ready to be all-reduced.  `out`: write into this tensor
