@@ -78,11 +78,8 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
         s_ray[32 + threadIdx.x] = p.ray_s[threadIdx.x % kBeams];
     }
     if (lane < 8) stat[lane] = 0.f;
-    // separating-axis pass: 4 steps at a time, 8 lanes each; a lane takes every 8th edge of the bank
-    constexpr int lps = 8, nslots = 4;
-    const int sslot = lane >> 3, sel = lane & 7;
-    const unsigned slotmask = 0xffu << (sslot * 8);
-    const int epl = (p.hull_max + lps - 1) / lps;
+    // separating-axis pass: one step per env group at a time, lane t takes bank edges t, t + T, ...
+    const int epl = (p.hull_max + T - 1) / T;
 
     const size_t act_esize = p.action_dtype == 1 ? 8 : (p.action_dtype == 2 ? 1 : 4);
     const char *act0 = reinterpret_cast<const char *>(p.actions) + (size_t)ec * act_esize;
@@ -135,28 +132,44 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
         int mrud;
         {
             float4 *ph = s_ph + (warp * 32 + gbase) * 2;
-            // scan 1: rudder, angular velocity, angle (these do not depend on the trig of the pose).  The action is
-            // decoded once per lane: low byte = rudder increment + 5 (Ship.rotate, models.py:136-146), bit 8 = thrust.
+            // scan 1a: the rudder (Ship.rotate / clamp_rudder, models.py:136-146) is an integer recurrence
+            // rud <- clamp(rud + inc, -10, 10).  Clamped additions are closed under composition --
+            // min(max(r + a, lo), hi) followed by (a', lo', hi') is (a + a', max(lo + a', lo'), min(max(hi + a', lo'), hi'))
+            // -- so the T rudder values of the window come from a log2(T)-round prefix over (a, lo, hi) instead of a
+            // T-step chain; integers, hence exact.
+            int rud_t;                                  // rudder after the action of step t
             {
-                const int dec = (a_my == 1 ? 0 : (a_my == 2 ? 10 : 5)) | (a_my == 0 ? 256 : 0);
+                int fa = a_my == 1 ? -5 : (a_my == 2 ? 5 : 0), flo = -10, fhi = 10;
+#pragma unroll
+                for (int off = 1; off < T; off <<= 1) {
+                    const int pa = __shfl_up_sync(kFull, fa, off, T), plo = __shfl_up_sync(kFull, flo, off, T),
+                              phi = __shfl_up_sync(kFull, fhi, off, T);
+                    if (t >= off) {                     // earlier steps first (pa, plo, phi), then this lane's
+                        const int na = pa + fa, nlo = max(plo + fa, flo), nhi = min(max(phi + fa, flo), fhi);
+                        fa = na; flo = nlo; fhi = nhi;
+                    }
+                }
+                rud_t = min(max(r.rudder + fa, flo), fhi);
+            }
+            // scan 1b: angular velocity and angle.  Thrust (action 0) leaves the rudder alone, so the torque term of
+            // step t uses rud_t; it is rounded to fp32 before the fused multiply-add, exactly as in step_kernel.
+            {
+                const float dw_t = a_my == 0 ? -p.ang_dt * (float)rud_t : 0.f;
                 float th = r.th, w = r.w;
-                int rud = r.rudder;
-                float4 *po = ph;
+                float2 *po = reinterpret_cast<float2 *>(ph);
 #pragma unroll 4
                 for (int i = 0; i < T; ++i) {
-                    const int d = __shfl_sync(kFull, dec, gbase + i);
-                    const float dw = (d & 256) ? -p.ang_dt * (float)rud : 0.f;
-                    rud = min(max(rud + (d & 255) - 5, -10), 10);    // clamp_rudder: rud is always within [-10, 10]
+                    const float dw = __shfl_sync(kFull, dw_t, i, T);
                     th += w * p.dt;
                     w = w * p.damping + dw;
-                    if (t == 0) *po = make_float4(th, w, __int_as_float(rud), 0.f);
-                    po += 2;
+                    if (t == 0) *po = make_float2(th, w);
+                    po += 4;
                 }
             }
             __syncwarp();
             {
-                const float4 v = ph[2 * t];
-                mth = v.x; mw = v.y; mrud = __float_as_int(v.z);
+                const float2 v = *reinterpret_cast<const float2 *>(ph + 2 * t);
+                mth = v.x; mw = v.y; mrud = rud_t;
             }
             sincos_fast(mth, ms, mc);                   // one sincos per lane instead of T per lane
             // thrust of step t acts along the heading the step STARTS from: the trig of step t-1 (or of the carry)
@@ -170,7 +183,7 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
                 float4 *po = ph + 1;
 #pragma unroll 4
                 for (int i = 0; i < T; ++i) {
-                    const float dvx = __shfl_sync(kFull, dvx_t, gbase + i), dvy = __shfl_sync(kFull, dvy_t, gbase + i);
+                    const float dvx = __shfl_sync(kFull, dvx_t, i, T), dvy = __shfl_sync(kFull, dvy_t, i, T);
                     x += vx * p.dt;
                     y += vy * p.dt;
                     vx = vx * p.damping + dvx;
@@ -258,28 +271,48 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
         }
         __syncwarp();
 
+        // ---- 3a. goals taken so far in the window: prefix OR of the touch masks (one ballot per goal: taken before /
+        // up to step t <=> an earlier / this-or-earlier lane of the env touches it)
+        unsigned inc = 0u, exc = 0u;
+        {
+            const unsigned below = segmask & ((1u << lane) - 1u), upto = segmask & ((2u << lane) - 1u);
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i) {
+                const unsigned m = __ballot_sync(kFull, (touch >> i) & 1u);
+                if (m & below) exc |= 1u << i;
+                if (m & upto) inc |= 1u << i;
+            }
+        }
+        const int alive_prev = r.alive & ~(int)exc, alive_t = r.alive & ~(int)inc;
+        const bool goal_reached = (alive_prev & (int)touch) != 0;
+        const int steps_t = r.steps + t + 1;
+        const bool all_goals = alive_t == 0;
+        const bool timeout = steps_t >= p.max_steps;
+        // With auto-reset the window is cut after the env's first done step, so nothing behind the first step that is done
+        // for a reason already known (no goals left, out of bounds, step cap) can be committed: such steps need neither
+        // the overlap test nor a lidar query.  (A ship that has run into a bank keeps ploughing through it for the rest of
+        // the speculated window: before this cut those steps were a third of the separating-axis work.)
+        const bool prune = p.auto_reset != 0;
+        bool asking = ask != 0u;
+        {
+            const unsigned cd = __ballot_sync(kFull, active && (all_goals || oob || timeout)) & segmask;
+            if (prune && cd != 0u && lane > __ffs(cd) - 1) asking = false;
+        }
+
         // ---- overlap test at the new pose -> collide_ship (game.py:232-241): separating-axis pass for the steps the
-        // plane phase could not settle (one lane per bank edge, 32/lps steps at a time)
+        // plane phase could not settle.  Every env group works on its own earliest open step (one lane per bank edge,
+        // strided when the hull has more edges than the group has lanes); a collision closes all later steps of the env.
         bool colliding = false;
         {
-            unsigned needs = __ballot_sync(kFull, ask != 0u);
-            while (needs) {
-                int src = -1, myslot = -1;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (q < nslots && needs) {
-                        const int tt = __ffs(needs) - 1;
-                        needs &= needs - 1u;
-                        if (sslot == q) src = tt;
-                        if (tt == lane) myslot = q;
-                    }
-                }
-                const bool act_env = src >= 0;
-                const int srcl = act_env ? src : lane;
-                const float bx = __shfl_sync(kFull, mx, srcl), by = __shfl_sync(kFull, my, srcl);
-                const float bc = __shfl_sync(kFull, mc, srcl), bs = __shfl_sync(kFull, ms, srcl);
-                const unsigned bsa = __shfl_sync(kFull, (unsigned)r.scen | (ask << 28), srcl);
-                const float4 *rec = p.bank + (size_t)(bsa & 0x0fffffffu) * p.scen_stride4;
+            unsigned needs;
+            while ((needs = __ballot_sync(kFull, asking)) != 0u) {
+                const unsigned mine = needs & segmask;
+                const bool act_env = mine != 0u;
+                const int src = act_env ? __ffs(mine) - 1 : lane;
+                const float bx = __shfl_sync(kFull, mx, src), by = __shfl_sync(kFull, my, src);
+                const float bc = __shfl_sync(kFull, mc, src), bs = __shfl_sync(kFull, ms, src);
+                const unsigned bask = __shfl_sync(kFull, ask, src);
+                const float4 *rec = p.bank + (size_t)r.scen * p.scen_stride4;
                 const float4 hdr = __ldg(rec + 4);
                 const float4 *bE = rec + kBankHeader4;
                 float rx[kShipVerts], ry[kShipVerts];
@@ -291,25 +324,25 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
                 bool coll = false;
 #pragma unroll 1
                 for (int b = 0; b < 2; ++b) {
-                    const bool do_b = act_env && ((bsa >> (28 + b)) & 1u) && !coll;
+                    const bool do_b = act_env && ((bask >> b) & 1u) && !coll;
                     const int nb = __float_as_int(b ? hdr.w : hdr.z);
                     const float4 *bEb = bE + b * p.maxv;
-                    // a bank edge normal separates?  (lane `sel` of the slot takes edges sel, sel + 8, ...)
+                    // a bank edge normal separates?  (lane t of the group takes edges t, t + T, ...)
                     bool lsep = false;
 #pragma unroll 1
                     for (int u = 0; u < epl; ++u) {
-                        const int idx = sel + u * lps;
+                        const int idx = t + u * T;
                         if (do_b && idx < nb) lsep = lsep || bank_axis_separates(__ldg(bEb + idx), rx, ry, bx, by);
                     }
                     const unsigned sb = __ballot_sync(kFull, lsep);
-                    bool sep = (sb & slotmask) != 0u;
+                    bool sep = (sb & segmask) != 0u;
                     if (__ballot_sync(kFull, do_b && !sep)) {                   // else try the ship's edge normals
                         float pr[kShipVerts];
 #pragma unroll
                         for (int j = 0; j < kShipVerts; ++j) pr[j] = 3.0e38f;
 #pragma unroll 1
                         for (int u = 0; u < epl; ++u) {
-                            const int idx = sel + u * lps;
+                            const int idx = t + u * T;
                             if (do_b && idx < nb) {
                                 const float4 ed = __ldg(bEb + idx);
 #pragma unroll
@@ -321,23 +354,33 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < kShipVerts; ++j) {      // axis j separates <=> no bank vertex of the slot reaches the hull's plane j
+                        for (int j = 0; j < kShipVerts; ++j) {      // axis j separates <=> no bank vertex reaches the hull's plane j
                             const unsigned reach = __ballot_sync(kFull, pr[j] <= p.ship_off[j]);
-                            sep = sep || (reach & slotmask) == 0u;
+                            sep = sep || (reach & segmask) == 0u;
                         }
                     }
                     if (do_b && !sep) coll = true;
                 }
-                const unsigned res = __ballot_sync(kFull, coll);
-                if (myslot >= 0 && ((res >> (myslot * lps)) & 1u)) colliding = true;
+                if (act_env && lane == src) { asking = false; colliding = coll; }
+                if (coll && prune) asking = false;                              // the env is done at step src: later steps are moot
             }
         }
 
+        // ShipEnv.determine_reward (ship_env.py:62-77) / is_done (ship_env.py:115-134)
+        const float reward = goal_reached ? 1.f : (oob ? -1.f : p.step_penalty);
+        const bool done = colliding || all_goals || oob || timeout;
+        // cut the window after the first done step (auto-reset): everything speculated beyond it is discarded
+        const unsigned dmask = __ballot_sync(kFull, active && done) & segmask;
+        const bool do_reset = p.auto_reset && dmask != 0u;
+        const int ncommit = do_reset ? __ffs(dmask) - gbase : nvalid;
+        const bool commit = t < ncommit;
+
         // ---- LiDAR.query (models.py:39-76) of step t at its PRE-integration pose = the pose of step t-1 (ring slot
-        // cb + t; the carry for t = 0).  Up to three needy steps per pass, lanes 0-9 / 10-19 / 20-29 = their rays.
+        // cb + t; the carry for t = 0), for the steps that are committed.  Up to three needy steps per pass, lanes 0-9 /
+        // 10-19 / 20-29 = their rays.
         {
             const int srcrow = sc0 + ring(cb + t) * kScr4;
-            const int hz_own = active ? __float_as_int(s_scr[srcrow].z) : 0;
+            const int hz_own = commit ? __float_as_int(s_scr[srcrow].z) : 0;
             const bool big = (hz_own & kHdrBig) != 0;
             const bool wants = (hz_own & 0x3ff) != 0;
             const unsigned need = __ballot_sync(kFull, wants);
@@ -376,37 +419,12 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
             }
         }
 
-        // ---- 3. the sequential leftovers.  Goals taken so far in the window: prefix OR of the touch masks.
-        // (one ballot per goal: taken before / up to step t <=> an earlier / this-or-earlier lane of the env touches it)
-        unsigned inc = 0u, exc = 0u;
-        {
-            const unsigned below = segmask & ((1u << lane) - 1u), upto = segmask & ((2u << lane) - 1u);
-#pragma unroll
-            for (int i = 0; i < kGoals; ++i) {
-                const unsigned m = __ballot_sync(kFull, (touch >> i) & 1u);
-                if (m & below) exc |= 1u << i;
-                if (m & upto) inc |= 1u << i;
-            }
-        }
-        const int alive_prev = r.alive & ~(int)exc, alive_t = r.alive & ~(int)inc;
-        const bool goal_reached = (alive_prev & (int)touch) != 0;
-        const int steps_t = r.steps + t + 1;
-        // ShipEnv.determine_reward (ship_env.py:62-77) / is_done (ship_env.py:115-134)
-        const float reward = goal_reached ? 1.f : (oob ? -1.f : p.step_penalty);
-        const bool all_goals = alive_t == 0;
-        const bool timeout = steps_t >= p.max_steps;
-        const bool done = colliding || all_goals || oob || timeout;
-        // cut the window after the first done step (auto-reset): everything speculated beyond it is discarded
-        const unsigned dmask = __ballot_sync(kFull, active && done) & segmask;
-        const bool do_reset = p.auto_reset && dmask != 0u;
-        const int ncommit = do_reset ? __ffs(dmask) - gbase : nvalid;
-        const bool commit = t < ncommit;
         // episode return after step t: ordered sum (lane t adds the rewards of steps 0..t one by one), same rounding
         // as one step at a time
         float my_ret = r.ret;
-#pragma unroll 8
+#pragma unroll
         for (int i = 0; i < T; ++i) {
-            const float rv = __shfl_sync(kFull, reward, gbase + i);
+            const float rv = __shfl_sync(kFull, reward, i, T);
             if (i <= t) my_ret += rv;
         }
         warp_stats(stat, lane, commit, goal_reached, done, colliding, oob, timeout, all_goals, my_ret, steps_t);
@@ -435,8 +453,7 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < kBeams; ++j) {
                 const unsigned m = __ballot_sync(kFull, h[j] != kMiss) & upto;
-                const int src = m ? 31 - __clz(m) : lane;
-                const float v = __shfl_sync(kFull, h[j], src);
+                const float v = __shfl_sync(kFull, h[j], 31 - __clz(m));     // m == 0: lane 31's value, not used
                 h[j] = m ? v : cv[j];
             }
             myfr[0] = make_float4(mx, my, (float)mrud, mth);
@@ -452,9 +469,10 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
         {
             const float4 *ph = s_ph + (warp * 32 + srcl) * 2;
             const float4 v0 = ph[0], v1 = ph[1];
-            rn.th = v0.x; rn.w = v0.y; rn.rudder = __float_as_int(v0.z);
+            rn.th = v0.x; rn.w = v0.y;
             rn.x = v1.x; rn.y = v1.y; rn.vx = v1.z; rn.vy = v1.w;
         }
+        rn.rudder = __shfl_sync(kFull, mrud, srcl);
         rn.ret = __shfl_sync(kFull, my_ret, srcl);
         rn.alive = __shfl_sync(kFull, alive_t, srcl);
         rn.steps = r.steps + ncommit; rn.scen = r.scen; rn.episode = r.episode;
