@@ -31,9 +31,14 @@
 namespace shipsim {
 
 constexpr int kWinThreads = 64;      // small CTAs: a latency-bound batch is a few hundred warps, spread them evenly over the SMs
+#ifdef SHIPSIM_WIN_MAXNREG
+#define SHIPSIM_WIN_BOUNDS __maxnreg__(SHIPSIM_WIN_MAXNREG)
+#else
+#define SHIPSIM_WIN_BOUNDS __launch_bounds__(kWinThreads, 8)
+#endif
 
 template <int T, int HIST>
-__global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_constant__ StepParams p)
+__global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int E = 32 / T;                   // envs per warp
     constexpr int NW = kWinThreads / 32;
@@ -114,8 +119,12 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
             else row[0] = make_float4(c0, s0, 0.f, 0.f);
         }
     }
-    int a_my = 3;
+    // Actions are held one window ahead: a_my = action of step k0 + t, a_nx = action of step k0 + T + t.  After a window
+    // that commits n steps the next window's actions are n lanes further along this pair (two shuffles); only the n
+    // lanes at the far end load anything, and what they load is not looked at before the end of the next window.
+    int a_my = 3, a_nx = 3;
     if (valid && t < p.K) a_my = load_action(p, act0 + (size_t)t * act_stride, t, gid);
+    if (valid && T + t < p.K) a_nx = load_action(p, act0 + (size_t)(T + t) * act_stride, T + t, gid);
     __syncthreads();
 
 #pragma unroll 1
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
         // ---- 2. pose-dependent work of step t at (mx, my, mth): reach-grid cell, candidate planes staged by cp.async
         const int myslot_ring = ring(cb + 1 + t);
         float4 *myrow = s_scr + sc0 + myslot_ring * kScr4;
-        float4 *myfr = s_frame + fr0 + myslot_ring * FS4;
+        float4 *myfr = s_frame + fr0 + (1 + t) * FS4;    // frames: slot 0 = carry, slot 1 + t = step t (no ring)
         float hx = 0.f, hy = 0.f;
         uint4 cell = make_uint4(0u, 0u, 0u, 0xffffffffu);
         if (active) {
@@ -387,7 +396,7 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
             if (big) ray_query_serial(p, s_scr + srcrow, reinterpret_cast<float *>(myfr) + 6);
             if (need) {
                 if (wants) s_src[warp][__popc(need & ((1u << lane) - 1u))] =
-                    (unsigned)(srcrow - wsc0) | ((unsigned)((fr0 - wfr0 + myslot_ring * FS4) * 4 + 6) << 16);
+                    (unsigned)(srcrow - wsc0) | ((unsigned)((fr0 - wfr0 + (1 + t) * FS4) * 4 + 6) << 16);
                 __syncwarp();
                 const int cnt = __popc(need);
                 const float ray_c = s_ray[lane], ray_s = s_ray[32 + lane];
@@ -439,7 +448,7 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
                 if (((alive_t >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
             float h[kBeams], cv[kBeams];
             {
-                const float4 *cf = s_frame + fr0 + cb * FS4;
+                const float4 *cf = s_frame + fr0;
                 const float2 a0 = reinterpret_cast<const float2 *>(cf + 1)[1];
                 const float4 a1 = cf[2], a2 = cf[3];
                 cv[0] = a0.x; cv[1] = a0.y; cv[2] = a1.x; cv[3] = a1.y; cv[4] = a1.z; cv[5] = a1.w;
@@ -497,27 +506,26 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
         }
         __syncwarp();
 
-        // ---- outputs of the committed steps.  Obs row of step t = [frame t-1 | frame t] = ring slots (cb+t, cb+t+1);
-        // OBS4 lanes per row, 32/OBS4 rows per round, 128-bit streaming stores.
+        // ---- outputs of the committed steps.  Obs row of step t = [frame t-1 | frame t] = frame slots (t, t + 1);
+        // OBS4 lanes per row, 32/OBS4 rows per store instruction, 128-bit streaming stores, no loop: a window has at
+        // most T rows per env.
         if (p.obs) {
-            constexpr int RPR = 32 / OBS4;                          // rows per round
+            constexpr int RPR = 32 / OBS4;                          // rows per store instruction
+            constexpr int NIT = (T + RPR - 1) / RPR;
             const float4 neg = make_float4(-1.f, -1.f, -1.f, -1.f);
             const int col = lane % OBS4, r0 = lane / OBS4;
             const int half = HIST == 2 ? (col >> 2) : 1, q = col & 3;
-            const size_t rstride = (size_t)p.N * OBS4;              // float4 between consecutive steps of one env
-#pragma unroll 1
+            const size_t rstride = (size_t)p.N * OBS4 * RPR;        // float4 between the rows of consecutive stores
+#pragma unroll
             for (int elr = 0; elr < E; ++elr) {
-                const int4 ev = s_env[warp * E + elr];              // k0, committed, carry slot, reset
-                const float4 *fb = s_frame + wfr0 + elr * FR4 + q;
+                const int4 ev = s_env[warp * E + elr];              // k0, committed, -, reset
+                const float4 *fb = s_frame + wfr0 + elr * FR4 + (r0 + half) * FS4 + q;
                 float4 *o = p.obs + ((size_t)(ev.x + r0) * p.N + (warp_env0 + elr)) * OBS4 + col;
-                int slot = ring(ev.z + r0 + half);
                 const int nplain = ev.w ? ev.y - 1 : ev.y;          // the last committed row of an env that resets is special
-#pragma unroll 2
-                for (int tr = r0; tr < nplain; tr += RPR) {
-                    __stcs(o, fb[slot * FS4]);
-                    o += rstride * RPR;
-                    slot += RPR;
-                    if (slot >= NS) slot -= NS;
+#pragma unroll
+                for (int it = 0; it < NIT; ++it) {
+                    if (r0 + it * RPR < nplain) __stcs(o, fb[it * RPR * FS4]);
+                    o += rstride;
                 }
                 if (ev.w && r0 == 0) {                              // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
                     const float4 rfv = (half == 0 || q >= 2) ? neg : s_rf[(warp * E + elr) * 2 + q];
@@ -534,11 +542,11 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
 
         if (ncommit > 0) {
             const int ncb = ring(cb + ncommit);
+            const float4 negc = make_float4(-1.f, -1.f, -1.f, -1.f);
             if (do_reset) {                     // carry := reset frame + the spawn pose's planes (built at scenario upload)
                 if (t == 0) {
-                    float4 *f = s_frame + fr0 + ncb * FS4;
-                    const float4 neg = make_float4(-1.f, -1.f, -1.f, -1.f);
-                    f[0] = s_rf[rf0]; f[1] = s_rf[rf0 + 1]; f[2] = neg; f[3] = neg;
+                    float4 *f = s_frame + fr0;
+                    f[0] = s_rf[rf0]; f[1] = s_rf[rf0 + 1]; f[2] = negc; f[3] = negc;
                 }
                 const float4 *sp = p.spawn_rows + (size_t)rn.scen * kScr4;
                 const float4 h0 = __ldg(sp);
@@ -546,20 +554,31 @@ __global__ void __launch_bounds__(kWinThreads, 8) window_kernel(const __grid_con
                 const int nrow = (hn & kHdrBig) ? 2 : 2 * (hn & 0xff);
                 float4 *row = s_scr + sc0 + ncb * kScr4;
                 for (int i = t; i <= nrow; i += T) row[i] = i == 0 ? h0 : __ldg(sp + i);
+            } else if (t == ncommit - 1) {      // carry := the frame of the last committed step
+                float4 *f = s_frame + fr0;
+                f[0] = myfr[0]; f[1] = myfr[1]; f[2] = myfr[2]; f[3] = myfr[3];
             }
             cb = ncb;
             r = rn; c0 = c0n; s0 = s0n;
             k0 += ncommit;
         }
-        a_my = 3;
-        if (valid && k0 + t < p.K) a_my = load_action(p, act0 + (size_t)(k0 + t) * act_stride, k0 + t, gid);
-        // the window after next starts somewhere in (k0, k0 + T]: pull its action rows into L2 now
-        if (p.action_dtype != 3 && valid && k0 + T + t < p.K) prefetch_l2(act0 + (size_t)(k0 + T + t) * act_stride);
+        {
+            const int sh = t + ncommit;                             // k0 has moved by ncommit (< = T)
+            const int m1 = __shfl_sync(kFull, a_my, sh, T), m2 = __shfl_sync(kFull, a_nx, sh, T);    // lane (sh mod T) of the group
+            a_my = sh < T ? m1 : m2;
+            a_nx = m2;
+            if (sh >= T) {
+                const int kk = k0 + T + t;
+                a_nx = (valid && kk < p.K) ? load_action(p, act0 + (size_t)kk * act_stride, kk, gid) : 3;
+            }
+            // two windows ahead: pull the action rows into L2
+            if (p.action_dtype != 3 && valid && k0 + 2 * T + t < p.K) prefetch_l2(act0 + (size_t)(k0 + 2 * T + t) * act_stride);
+        }
         __syncwarp();
     }
 
     if (valid && t == 0) {
-        const float4 *f = s_frame + fr0 + cb * FS4;
+        const float4 *f = s_frame + fr0;
         const float4 l1 = f[1], l2 = f[2], l3 = f[3];
         store_env(p, e, r, make_float4(l1.z, l1.w, l2.x, l2.y), make_float4(l2.z, l2.w, l3.x, l3.y), l3.z, l3.w);
         if (goals_dirty) {
