@@ -103,7 +103,7 @@ typedef struct shipsim_config {
 } shipsim_config;
 
 /* num_envs up to which steps_in_flight = 0 selects the time-parallel kernel (measured on B200, profiles/) */
-#define SHIPSIM_WINDOW_AUTO_MAX_ENVS 16384
+#define SHIPSIM_WINDOW_AUTO_MAX_ENVS 32768
 
 typedef struct shipsim_handle shipsim_t;
 

@@ -288,12 +288,13 @@ extern "C" int shipsim_create(const shipsim_config *cfg, int device, shipsim_t *
     if (cfg->steps_in_flight) {
         h->window = cfg->steps_in_flight;
     } else {
-        // Auto (measured on B200, profiles/r01_f_sweep_window.log): batches too small to fill the machine are bound by
+        // Auto (measured on B200, profiles/r01_k_sweep_window.log): batches too small to fill the machine are bound by
         // the latency of one dependent step after another; the window kernel speculates several steps of an env at
-        // once (shipsim_window.cu).  It pays until about 64K (env, step) lanes are in flight; beyond 16,384 envs the
-        // serial-in-time kernel is faster.  An explicit lanes_per_env asks for the serial-in-time kernel.
+        // once (shipsim_window.cu).  The window is as long as still lets every warp be resident at once (16 warps of
+        // 128 registers per SM x 148 SMs = 2,368 warps of 32 / T envs); beyond 32,768 envs the serial-in-time kernel
+        // is faster.  An explicit lanes_per_env asks for the serial-in-time kernel.
         const int n = cfg->num_envs;
-        h->window = (cfg->lanes_per_env || n > SHIPSIM_WINDOW_AUTO_MAX_ENVS) ? 1 : (n <= 2048 ? 32 : (n <= 6144 ? 16 : 8));
+        h->window = (cfg->lanes_per_env || n > SHIPSIM_WINDOW_AUTO_MAX_ENVS) ? 1 : (n <= 2368 ? 32 : (n <= 4736 ? 16 : 8));
     }
     *out = h;
     return SHIPSIM_OK;
