@@ -122,6 +122,11 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
     // Actions are held one window ahead: a_my = action of step k0 + t, a_nx = action of step k0 + T + t.  After a window
     // that commits n steps the next window's actions are n lanes further along this pair (two shuffles); only the n
     // lanes at the far end load anything, and what they load is not looked at before the end of the next window.
+    // The scenario of the NEXT episode depends only on (seed, env id, episode number): it is drawn an episode ahead, so
+    // that at a reset the Philox rounds are not in front of the loads of the new scenario's goals and spawn row, and
+    // every window pulls those few lines towards L1 in case it ends in a reset.
+    constexpr int SPL = (kScr4 + T - 1) / T;    // spawn-row float4s per lane
+    int next_scen = pick_scenario(p, gid, r.episode + 1);
     int a_my = 3, a_nx = 3;
     if (valid && t < p.K) a_my = load_action(p, act0 + (size_t)t * act_stride, t, gid);
     if (valid && T + t < p.K) a_nx = load_action(p, act0 + (size_t)(T + t) * act_stride, T + t, gid);
@@ -132,6 +137,14 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
         const int nvalid = valid ? min(T, p.K - k0) : 0;        // steps this env still has, capped by the window
         if (__ballot_sync(kFull, nvalid > 0) == 0u) break;
         const bool active = t < nvalid;
+        if (p.auto_reset) {
+#pragma unroll
+            for (int i = 0; i < (3 + kScr4 + T - 1) / T; ++i) {
+                const int q = t + i * T;
+                if (q < 3) prefetch_l1(p.bank + (size_t)next_scen * p.scen_stride4 + 2 + q);
+                else if (q < 3 + kScr4) prefetch_l1(p.spawn_rows + (size_t)next_scen * kScr4 + (q - 3));
+            }
+        }
 
         // ---- 1. the sequential part, T steps: handle_discrete_action (game.py:140-153), cpBodyUpdatePosition,
         // cpBodyUpdateVelocity -- the same operations in the same order as step_kernel, split so that as little as
@@ -223,7 +236,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
         // still alive is settled by the scan below)
         float2 g[kGoals];
         float gd2[kGoals];
-        unsigned touch = 0u;
+        unsigned touch = 0u, cand = 0u;
         {
 #pragma unroll
             for (int i = 0; i < kGoals; ++i) {
@@ -231,19 +244,9 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
                 const float ux = g[i].x - mx, uy = g[i].y - my;
                 gd2[i] = ux * ux + uy * uy;
             }
-            unsigned cand = 0u;
 #pragma unroll
             for (int i = 0; i < kGoals; ++i)
                 if (active && ((r.alive >> i) & 1) && gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
-#pragma unroll 1
-            while (cand) {
-                const int i = __ffs(cand) - 1;
-                cand &= cand - 1u;
-                const float2 gi = s_goal[goal0 + i];
-                const float ux = gi.x - mx, uy = gi.y - my;
-                const float qx = ux * mc + uy * ms, qy = -ux * ms + uy * mc;
-                if (goal_contact(p, qx, qy)) touch |= 1u << i;
-            }
         }
         // this step's lidar slots: "no hit" until the ray pass says otherwise
         reinterpret_cast<float2 *>(myfr + 1)[1] = make_float2(kMiss, kMiss);
@@ -264,21 +267,16 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
             }
         }
         const bool oob = (mx < 0.f) || (mx > p.W) || (my < 0.f) || (my > p.H);
-
-        // ---- plane phase at pose t: lidar planes of step t+1 + ship-vs-bank pre-test of step t
-        cp_async_wait_all();
-        unsigned ask = 0u;
-        if (staged) {
-            ask = plane_phase<true, true>(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow, myrow + 1);
-        } else if (near_any) {                  // more candidates than a row holds: rays are cast serially, full SAT pass
-            myrow[0] = make_float4(mc, ms, __int_as_float(kHdrBig), 0.f);
-            myrow[1] = make_float4(mx, my, hx, hy);
-            myrow[2] = make_float4(__int_as_float(r.scen), __uint_as_float(cell.x), __uint_as_float(cell.y), __uint_as_float(cell.z));
-            ask = ((cell.x != 0u || (cell.z & 1u)) ? 1u : 0u) | ((cell.y != 0u || (cell.z & 2u)) ? 2u : 0u);
-        } else if (active) {
-            myrow[0] = make_float4(mc, ms, 0.f, 0.f);
+        // (while the candidate planes are in flight: the exact goal tests and everything that follows from them)
+#pragma unroll 1
+        while (cand) {
+            const int i = __ffs(cand) - 1;
+            cand &= cand - 1u;
+            const float2 gi = s_goal[goal0 + i];
+            const float ux = gi.x - mx, uy = gi.y - my;
+            const float qx = ux * mc + uy * ms, qy = -ux * ms + uy * mc;
+            if (goal_contact(p, qx, qy)) touch |= 1u << i;
         }
-        __syncwarp();
 
         // ---- 3a. goals taken so far in the window: prefix OR of the touch masks (one ballot per goal: taken before /
         // up to step t <=> an earlier / this-or-earlier lane of the env touches it)
@@ -302,16 +300,33 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
         // the overlap test nor a lidar query.  (A ship that has run into a bank keeps ploughing through it for the rest of
         // the speculated window: before this cut those steps were a third of the separating-axis work.)
         const bool prune = p.auto_reset != 0;
-        bool asking = ask != 0u;
+        bool open_step = true;
         {
             const unsigned cd = __ballot_sync(kFull, active && (all_goals || oob || timeout)) & segmask;
-            if (prune && cd != 0u && lane > __ffs(cd) - 1) asking = false;
+            if (prune && cd != 0u && lane > __ffs(cd) - 1) open_step = false;
         }
+
+
+        // ---- plane phase at pose t: lidar planes of step t+1 + ship-vs-bank pre-test of step t
+        cp_async_wait_all();
+        unsigned ask = 0u;
+        if (staged) {
+            ask = plane_phase<true, true>(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow, myrow + 1);
+        } else if (near_any) {                  // more candidates than a row holds: rays are cast serially, full SAT pass
+            myrow[0] = make_float4(mc, ms, __int_as_float(kHdrBig), 0.f);
+            myrow[1] = make_float4(mx, my, hx, hy);
+            myrow[2] = make_float4(__int_as_float(r.scen), __uint_as_float(cell.x), __uint_as_float(cell.y), __uint_as_float(cell.z));
+            ask = ((cell.x != 0u || (cell.z & 1u)) ? 1u : 0u) | ((cell.y != 0u || (cell.z & 2u)) ? 2u : 0u);
+        } else if (active) {
+            myrow[0] = make_float4(mc, ms, 0.f, 0.f);
+        }
+        __syncwarp();
 
         // ---- overlap test at the new pose -> collide_ship (game.py:232-241): separating-axis pass for the steps the
         // plane phase could not settle.  Every env group works on its own earliest open step (one lane per bank edge,
         // strided when the hull has more edges than the group has lanes); a collision closes all later steps of the env.
         bool colliding = false;
+        bool asking = ask != 0u && open_step;
         {
             unsigned needs;
             while ((needs = __ballot_sync(kFull, asking)) != 0u) {
@@ -487,13 +502,19 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
         rn.steps = r.steps + ncommit; rn.scen = r.scen; rn.episode = r.episode;
         float c0n = __shfl_sync(kFull, mc, srcl), s0n = __shfl_sync(kFull, ms, srcl);
         if (t == 0) s_env[warp * E + el] = make_int4(k0, ncommit, cb, (int)do_reset);
+        float4 spv[SPL];                                            // the new scenario's spawn row, lane t holds entries t, t + T, ...
         if (do_reset) {                                             // ShipEnv.reset (ship_env.py:171-184)
             const int ep = r.episode + 1;
-            reset_env(p, rn, pick_scenario(p, gid, ep), ep);
+            reset_env(p, rn, next_scen, ep);
             c0n = 1.f; s0n = 0.f;
             const float4 *rec = p.bank + (size_t)rn.scen * p.scen_stride4;
+            const float4 *sp = p.spawn_rows + (size_t)rn.scen * kScr4;
+            const float4 rg0 = __ldg(rec + 2), rg1 = __ldg(rec + 3), rg2 = __ldg(rec + 4);
+#pragma unroll
+            for (int i = 0; i < SPL; ++i) if (t + i * T < kScr4) spv[i] = __ldg(sp + t + i * T);
+            next_scen = pick_scenario(p, gid, ep + 1);
             float2 gn[kGoals];
-            unpack_goals(__ldg(rec + 2), __ldg(rec + 3), __ldg(rec + 4), gn);
+            unpack_goals(rg0, rg1, rg2, gn);
             float rgx, rgy;
             closest_goal(gn, rn.alive, rn.x, rn.y, rgx, rgy);
             if (t == 0) {
@@ -548,12 +569,9 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
                     float4 *f = s_frame + fr0;
                     f[0] = s_rf[rf0]; f[1] = s_rf[rf0 + 1]; f[2] = negc; f[3] = negc;
                 }
-                const float4 *sp = p.spawn_rows + (size_t)rn.scen * kScr4;
-                const float4 h0 = __ldg(sp);
-                const int hn = __float_as_int(h0.z);
-                const int nrow = (hn & kHdrBig) ? 2 : 2 * (hn & 0xff);
-                float4 *row = s_scr + sc0 + ncb * kScr4;
-                for (int i = t; i <= nrow; i += T) row[i] = i == 0 ? h0 : __ldg(sp + i);
+                float4 *row = s_scr + sc0 + ncb * kScr4;            // the whole row: entries past its planes are never read
+#pragma unroll
+                for (int i = 0; i < SPL; ++i) if (t + i * T < kScr4) row[t + i * T] = spv[i];
             } else if (t == ncommit - 1) {      // carry := the frame of the last committed step
                 float4 *f = s_frame + fr0;
                 f[0] = myfr[0]; f[1] = myfr[1]; f[2] = myfr[2]; f[3] = myfr[3];
