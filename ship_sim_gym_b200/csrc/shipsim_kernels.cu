@@ -97,7 +97,6 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
     sincos_fast(r.th, s, c);
     hull_half_extents(p, c, s, hx, hy);
     uint4 cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
-    bool goals_dirty = false;
     const size_t act_esize = p.action_dtype == 1 ? 8 : (p.action_dtype == 2 ? 1 : 4);
     const size_t act_stride = (size_t)p.N * act_esize;
     const char *ap = reinterpret_cast<const char *>(p.actions) + (size_t)(valid ? e : p.N - 1) * act_esize;
@@ -211,6 +210,8 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                 const float ux = g[i].x - r.x, uy = g[i].y - r.y;
                 gd2[i] = ux * ux + uy * uy;
             }
+            const int alive_before = r.alive;          // goal_reached <=> a goal was taken (a separate flag set inside the loops
+                                                       // below ended up in local memory at G = 1)
             if (G == 1) {
                 // throughput-bound batches: goals inside the hull's bounding circle are tested one per loop trip (a lane
                 // rarely has more than one), then the nearest REMAINING goal is picked once for the frame
@@ -225,8 +226,9 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                     const float2 gi = s_goal[goal0 + i * EPW];
                     const float ux = gi.x - r.x, uy = gi.y - r.y;
                     const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
-                    if (goal_contact(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << i); }
+                    if (goal_contact(p, qx, qy)) r.alive &= ~(1 << i);
                 }
+                goal_reached = r.alive != alive_before;
                 float best = 3.0e38f;
 #pragma unroll
                 for (int i = 0; i < kGoals; ++i)
@@ -245,8 +247,9 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                     for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
                     ux -= r.x; uy -= r.y;
                     const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
-                    if (goal_contact(p, qx, qy)) { goal_reached = true; r.alive &= ~(1 << i); }
+                    if (goal_contact(p, qx, qy)) r.alive &= ~(1 << i);
                 }
+                goal_reached = r.alive != alive_before;
                 float best = 3.0e38f;
 #pragma unroll
                 for (int i = 0; i < kGoals; ++i)
@@ -355,14 +358,17 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                     {
                         const float4 *rec = p.bank + (size_t)r.scen * p.scen_stride4;
                         float2 g[kGoals];
-                        unpack_goals(__ldg(rec + 2), __ldg(rec + 3), __ldg(rec + 4), g);
+                        const float4 rg0 = __ldg(rec + 2), rg1 = __ldg(rec + 3), rg2 = __ldg(rec + 4);
+                        unpack_goals(rg0, rg1, rg2, g);
                         closest_goal(g, r.alive, r.x, r.y, gx, gy);
                         if (gl == 0) {
 #pragma unroll
                             for (int i = 0; i < kGoals; ++i) s_goal[goal0 + i * EPW] = g[i];
                         }
+                        // the goal planes of the state change only here: written at once (a "goals changed" flag carried
+                        // to the end of the kernel had been spilled to local memory and reloaded every iteration)
+                        if (leader) store_goals(p, e, rg0, rg1, rg2);
                     }
-                    goals_dirty = true;
                     if (gl == 0) {              // the spawn pose's planes were evaluated when the scenario was loaded
                         const float4 *sp = p.spawn_rows + (size_t)r.scen * kScr4;
                         const float4 h0 = __ldg(sp);
@@ -426,11 +432,6 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
     if (leader) {
         const float4 l1 = row4[OBS4 - 3], l2 = row4[OBS4 - 2], l3 = row4[OBS4 - 1];
         store_env(p, e, r, make_float4(l1.z, l1.w, l2.x, l2.y), make_float4(l2.z, l2.w, l3.x, l3.y), l3.z, l3.w);
-        if (goals_dirty) {
-            const float2 a0 = s_goal[goal0], a1 = s_goal[goal0 + EPW], a2 = s_goal[goal0 + 2 * EPW], a3 = s_goal[goal0 + 3 * EPW],
-                         a4 = s_goal[goal0 + 4 * EPW];
-            store_goals(p, e, make_float4(a0.x, a0.y, a1.x, a1.y), make_float4(a2.x, a2.y, a3.x, a3.y), make_float4(a4.x, a4.y, 0.f, 0.f));
-        }
     }
 #undef row4
 #undef myscr
