@@ -110,7 +110,12 @@ constexpr int kHdrIn0 = 1 << 8, kHdrIn1 = 1 << 9, kHdrBig = 1 << 10;
 //   big row (more than kMaxCand candidates; rays are then cast serially by the owner lane):
 //   [1]      x, y, hx, hy               [2]     bits(scen), bits(m0), bits(m1), bits(flags)
 // STAGED: the raw EdgeD record of candidate i has already been copied (cp.async) into raw[2i], raw[2i+1]; the
-// record carries its own index (bank * kMaxHull + edge) in `pad`, so the candidate masks need not be walked again.
+// record carries its own index (bank * kMaxHull + edge) in `pad`, so the candidate masks need not be walked again
+// (only cells with at most kMaxCand candidates are staged).
+// A cell may name more than kMaxCand candidates (long banks of short edges: the hard map): all of them are evaluated
+// -- the separating-plane pre-test and the inside test want every one -- and since the fan-reach cull drops about half,
+// the row usually still holds what the rays can reach.  Only when a (kMaxCand+1)-th plane would have to be kept does
+// the env fall back to the big row (serial ray query by the owner lane).
 template <bool WITH_SAT, bool STAGED>
 __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, float y, float hx, float hy, float c, float s, int scen,
                                                 const uint4 cell, float4 *row, const float4 *raw = nullptr)
@@ -118,17 +123,19 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
     unsigned m0 = cell.x, m1 = cell.y;
     const unsigned near = ((m0 != 0u || (cell.z & 1u)) ? 1u : 0u) | ((m1 != 0u || (cell.z & 2u)) ? 2u : 0u);
     const int ncand = (int)((cell.z >> 8) & 0xffu);
-    if (ncand > kMaxCand) {
-        row[0] = make_float4(c, s, __int_as_float(kHdrBig), 0.f);
-        row[1] = make_float4(x, y, hx, hy);
-        row[2] = make_float4(__int_as_float(scen), __uint_as_float(m0), __uint_as_float(m1), __uint_as_float(cell.z));
-        return near;
-    }
     const float L = p.lidar_len;
     const EdgeD *E = p.edges_d + (size_t)scen * (2 * kMaxHull);
     const double xd = (double)x, yd = (double)y, hxd = (double)hx, hyd = (double)hy;
     unsigned outm = 0u, sepm = 0u;
     int nk = 0;                                  // planes kept for the ray pass
+    double2 nd_next = make_double2(0.0, 0.0);
+    float4 ev_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!STAGED && ncand > 0) {
+        int idx;
+        if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
+        nd_next = __ldg(reinterpret_cast<const double2 *>(E + idx));
+        ev_next = __ldg(reinterpret_cast<const float4 *>(E + idx) + 1);
+    }
 #pragma unroll 1
     for (int n = 0; n < ncand; ++n) {
         double2 nd;
@@ -136,11 +143,14 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
         if (STAGED) {
             nd = *reinterpret_cast<const double2 *>(raw + 2 * n);
             ev = raw[2 * n + 1];
-        } else {
-            int idx;
-            if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
-            nd = __ldg(reinterpret_cast<const double2 *>(E + idx));
-            ev = __ldg(reinterpret_cast<const float4 *>(E + idx) + 1);
+        } else {                                 // the next record is asked for before this one is evaluated
+            nd = nd_next; ev = ev_next;
+            if (n + 1 < ncand) {
+                int idx;
+                if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
+                nd_next = __ldg(reinterpret_cast<const double2 *>(E + idx));
+                ev_next = __ldg(reinterpret_cast<const float4 *>(E + idx) + 1);
+            }
         }
         const bool bank1 = __float_as_int(ev.w) >= kMaxHull;
         const unsigned bbit = bank1 ? 2u : 1u;
@@ -163,6 +173,12 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
         float reach = 1.f;
         if (cm < p.fan_cos) reach = cm * p.fan_cos + sqrt_approx(fmaxf(1.f - cm * cm, 0.f)) * p.fan_sin;    // a bound: approx is plenty
         if (pe.d >= 0.f && pe.d <= L * reach * 1.0001f + 1.0e-3f) {
+            if (!STAGED && nk == kMaxCand) {     // the row is full: big row (the masks are the cell's, not the walked ones)
+                row[0] = make_float4(c, s, __int_as_float(kHdrBig), 0.f);
+                row[1] = make_float4(x, y, hx, hy);
+                row[2] = make_float4(__int_as_float(scen), __uint_as_float(cell.x), __uint_as_float(cell.y), __uint_as_float(cell.z));
+                return near & ~sepm;            // what has been proven separated stays proven
+            }
             row[1 + 2 * nk] = make_float4(pe.d, pe.ta, -L * pe.nx, -L * pe.ny);
             row[2 + 2 * nk] = make_float4(pe.len, bank1 ? 1.f : 0.f, 0.f, 0.f);
             ++nk;
@@ -174,7 +190,15 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
     return near & ~sepm;
 }
 
-// Serial LiDAR.query of one env by one lane: only for cells with more than kMaxCand candidate planes.
+// The plane phase for cells that name more candidates than are staged, out of line: it walks the candidate masks and
+// reads the records from global memory.  (Inlined into the window kernel it cost registers the hot path needs.)
+static __device__ __noinline__ unsigned plane_phase_unstaged(const StepParams &p, float x, float y, float hx, float hy, float c, float s,
+                                                             int scen, const uint4 cell, float4 *row)
+{
+    return plane_phase<true, false>(p, x, y, hx, hy, c, s, scen, cell, row);
+}
+
+// Serial LiDAR.query of one env by one lane: only for rows that more than kMaxCand planes would have to be kept in.
 static __device__ __noinline__ void ray_query_serial(const StepParams &p, const float4 *row, float *lid)
 {
     const float L = p.lidar_len;

@@ -27,6 +27,9 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
 {
     constexpr int EPW = 32 / G;                 // envs per warp
     constexpr int OBS4 = 4 * HIST;              // float4 per obs row
+    // ray pass: two passes (six envs) per loop trip in the 128-register build (grids that do not fill the machine are
+    // latency bound: +4 % on the hard map at 65,536 envs); the 96-register build has no room for it (-1 % at 1M envs)
+    constexpr int kRayPassUnroll = MINB <= 4 ? 2 : 1;
     constexpr int ROW4 = OBS4 + 1;              // padded tile row (odd float4 stride: conflict-free 128-bit accesses)
     constexpr int CF = 16 * (HIST - 1);         // float offset of the newest frame inside a row
     constexpr int NW = kThreads / 32;
@@ -153,7 +156,7 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                 __syncwarp();
                 const int cnt = __popc(need);
                 const float ray_c = s_ray[lane], ray_s = s_ray[32 + lane];
-#pragma unroll 1
+#pragma unroll kRayPassUnroll
                 for (int q = rslot; q < cnt; q += 3) {          // lanes 30, 31 (rslot 3) only keep the others company
                     if (rslot < 3) {
                         const int env = s_src[warp][q];

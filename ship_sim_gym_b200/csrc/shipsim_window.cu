@@ -312,11 +312,8 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
         unsigned ask = 0u;
         if (staged) {
             ask = plane_phase<true, true>(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow, myrow + 1);
-        } else if (near_any) {                  // more candidates than a row holds: rays are cast serially, full SAT pass
-            myrow[0] = make_float4(mc, ms, __int_as_float(kHdrBig), 0.f);
-            myrow[1] = make_float4(mx, my, hx, hy);
-            myrow[2] = make_float4(__int_as_float(r.scen), __uint_as_float(cell.x), __uint_as_float(cell.y), __uint_as_float(cell.z));
-            ask = ((cell.x != 0u || (cell.z & 1u)) ? 1u : 0u) | ((cell.y != 0u || (cell.z & 2u)) ? 2u : 0u);
+        } else if (near_any) {                  // more candidates than are staged: evaluated straight from global memory
+            ask = plane_phase_unstaged(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow);
         } else if (active) {
             myrow[0] = make_float4(mc, ms, 0.f, 0.f);
         }

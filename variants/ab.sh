@@ -1,8 +1,10 @@
 #!/bin/bash
-# A/B of kernel variants: variants/lib_*.so against the in-tree library, two rounds
 for round in 1 2; do
-  python profiles/prof_driver.py --envs 4096 --K 1000 --reps 20 | sed "s/^/base /"
-  for f in variants/lib_*.so; do
-    SHIPSIM_LIB=$PWD/$f python profiles/prof_driver.py --envs 4096 --K 1000 --reps 20 | sed "s|^|$(basename $f) |"
+  for f in base variants/lib_*.so; do
+    if [ $f = base ]; then unset SHIPSIM_LIB; else export SHIPSIM_LIB=$PWD/$f; fi
+    echo "$(basename $f) hard: $(python profiles/prof_driver.py --envs 65536 --K 100 --reps 10 --window 1 --hard | cut -c1-70)"
+    echo "$(basename $f) 1M:   $(python profiles/prof_driver.py --envs 1048576 --K 32 --reps 10 --window 1 | cut -c1-70)"
   done
 done
+unset SHIPSIM_LIB
+for i in 1 2 3; do python profiles/prof_driver.py --envs 4096 --K 1000 --reps 20 | cut -c1-70; done
