@@ -1,5 +1,6 @@
 #!/bin/bash
-for round in 1 2; do
+# A/B of kernel variants on the GPU box: build alternates with `nvcc ... -D<MACRO> -o variants/lib_<name>.so` (the
+# .so files are git-ignored but travel with gpurun), then `bash profiles/ab_variants.sh`; SHIPSIM_LIB selects the library.
   for f in base variants/lib_*.so; do
     if [ $f = base ]; then unset SHIPSIM_LIB; else export SHIPSIM_LIB=$PWD/$f; fi
     echo "$(basename $f) hard: $(python profiles/prof_driver.py --envs 65536 --K 100 --reps 10 --window 1 --hard | cut -c1-70)"
