@@ -31,7 +31,15 @@ class MlpPolicy(nn.Module):
 
 
 class RolloutCollector(object):
-    """Collects T-step rollouts of a BatchedShipEnv under a policy, entirely on the device."""
+    """Collects T-step rollouts of a BatchedShipEnv under a policy, entirely on the device.
+
+    The loop is launch bound (16,384 envs: every kernel in it runs for a few microseconds), so it is written to launch
+    as little as possible per step.  For an `MlpPolicy` the two trunks run as ONE three-layer network -- layer 1
+    side by side (the observation scale folded into its weights), layers 2 and 3 block-diagonal -- through `addmm`
+    into preallocated buffers: 3 GEMMs + 2 tanh per step instead of 6 + 4 + 1; the Gumbel noise of the whole rollout is
+    drawn once; log-probabilities, values and the GAE deltas are computed for all steps at once after the loop, which
+    leaves one fused multiply-add per step for the GAE recurrence.  Per step: 7 torch kernels + the env kernel.
+    Any other policy module (`forward(obs) -> (logits, value)`) takes the generic per-step path."""
 
     def __init__(self, env, policy, T=128, gamma=0.99, lam=0.95, use_graph=True):
         assert isinstance(env, BatchedShipEnv) and env.history <= 2
@@ -48,30 +56,87 @@ class RolloutCollector(object):
         self.returns = torch.empty(T, N, **f32)
         self.use_graph = bool(use_graph)
         self._graph = None
+        self._fused = isinstance(policy, MlpPolicy)
+        if self._fused:
+            lin = [policy.pi[0], policy.pi[2], policy.pi[4], policy.vf[0], policy.vf[2], policy.vf[4]]
+            H, A = lin[0].out_features, lin[2].out_features
+            assert lin[0].in_features == D and lin[3].out_features == H and lin[5].out_features == 1
+            self._H, self._A = H, A
+            self._W1, self._b1 = torch.empty(D, 2 * H, **f32), torch.empty(2 * H, **f32)
+            self._alloc_fused(N, D, H, A, T, f32)
+            self._z = torch.empty(N, A, **f32)
+        self._noise = torch.empty(T, N, policy.pi[4].out_features if self._fused else 3, **f32)
+        self._nonterm = torch.empty(T, N, **f32)
+        self._coef = torch.empty(T, N, **f32)
+        self._delta = torch.empty(T, N, **f32)
         env.validate_actions = False                            # the range check would need a host sync per step
         self.obs[0].copy_(env.reset())
+
+    def _alloc_fused(self, N, D, H, A, T, f32):
+        self._H, self._A = H, A
+        self._W1, self._b1 = torch.empty(D, 2 * H, **f32), torch.empty(2 * H, **f32)             # [pi | vf] side by side
+        self._W2, self._b2 = torch.zeros(2 * H, 2 * H, **f32), torch.empty(2 * H, **f32)           # block-diagonal
+        self._W3, self._b3 = torch.zeros(2 * H, A + 1, **f32), torch.empty(A + 1, **f32)           # pi -> columns 0..A-1, vf -> column A
+        self._h1, self._h2 = torch.empty(N, 2 * H, **f32), torch.empty(N, 2 * H, **f32)
+        self._out = torch.empty(T + 1, N, A + 1, **f32)         # logits | value of every step
+
+    def _refresh_fused(self):
+        """The policy's current parameters, laid out as one network (weights transposed for x @ W)."""
+        pi, vf, H, A = self.policy.pi, self.policy.vf, self._H, self._A
+        self._W1[:, :H].copy_(pi[0].weight.t()); self._W1[:, H:].copy_(vf[0].weight.t())
+        self._W1.mul_(self.policy.obs_scale)
+        self._b1[:H].copy_(pi[0].bias); self._b1[H:].copy_(vf[0].bias)
+        self._W2[:H, :H].copy_(pi[2].weight.t()); self._W2[H:, H:].copy_(vf[2].weight.t())
+        self._b2[:H].copy_(pi[2].bias); self._b2[H:].copy_(vf[2].bias)
+        self._W3[:H, :A].copy_(pi[4].weight.t()); self._W3[H:, A:].copy_(vf[4].weight.t())
+        self._b3[:A].copy_(pi[4].bias); self._b3[A:].copy_(vf[4].bias)
+
+    def _forward_fused(self, t):
+        """Three GEMMs and two tanh for both trunks.  (Two-entry batched GEMMs for layers 2 and 3, which skip the zero
+        blocks, were measured and are slower at 16,384 envs: 8.8 against 8.5 ms per 128-step rollout.)"""
+        torch.addmm(self._b1, self.obs[t], self._W1, out=self._h1).tanh_()
+        torch.addmm(self._b2, self._h1, self._W2, out=self._h2).tanh_()
+        torch.addmm(self._b3, self._h2, self._W3, out=self._out[t])
 
     @torch.no_grad()
     def _collect(self):
         env, T = self.env, self.T
-        for t in range(T):
-            logits, v = self.policy(self.obs[t])
-            # categorical sample by Gumbel-max: no host sync, graph-capturable
-            u = torch.rand_like(logits).clamp_(1e-10, 1.0)
-            a = torch.argmax(logits - torch.log(-torch.log(u)), dim=-1)
-            self.actions[t].copy_(a)
-            self.logp[t].copy_(torch.log_softmax(logits, dim=-1).gather(-1, a[:, None]).squeeze(-1))
-            self.values[t].copy_(v)
-            env.rollout(self.actions[t:t + 1], out=(self.obs[t + 1:t + 2], self.rewards[t:t + 1], self.dones[t:t + 1]))
-        _, v = self.policy(self.obs[T])
-        self.values[T].copy_(v)
-        # GAE(lambda), as PPO2 computes it
-        last = torch.zeros_like(self.values[0])
-        for t in range(T - 1, -1, -1):
-            nonterminal = 1.0 - self.dones[t].float()
-            delta = self.rewards[t] + self.gamma * self.values[t + 1] * nonterminal - self.values[t]
-            last = delta + self.gamma * self.lam * nonterminal * last
-            self.adv[t].copy_(last)
+        # categorical sampling by Gumbel-max (no host sync, graph-capturable): the noise of the whole rollout at once
+        self._noise.uniform_().clamp_(1e-10, 1.0).log_().neg_().log_().neg_()
+        if self._fused:
+            A = self._A
+            self._refresh_fused()
+            for t in range(T):
+                self._forward_fused(t)
+                torch.add(self._out[t, :, :A], self._noise[t], out=self._z)
+                torch.argmax(self._z, dim=-1, out=self.actions[t])
+                env.rollout(self.actions[t:t + 1], out=(self.obs[t + 1:t + 2], self.rewards[t:t + 1], self.dones[t:t + 1]))
+            self._forward_fused(T)
+            self.values.copy_(self._out[:, :, A])
+            self.logp.copy_(torch.log_softmax(self._out[:T, :, :A], dim=-1).gather(-1, self.actions[:, :, None]).squeeze(-1))
+        else:
+            for t in range(T):
+                logits, v = self.policy(self.obs[t])
+                a = torch.argmax(logits + self._noise[t], dim=-1)
+                self.actions[t].copy_(a)
+                self.logp[t].copy_(torch.log_softmax(logits, dim=-1).gather(-1, a[:, None]).squeeze(-1))
+                self.values[t].copy_(v)
+                env.rollout(self.actions[t:t + 1], out=(self.obs[t + 1:t + 2], self.rewards[t:t + 1], self.dones[t:t + 1]))
+            _, v = self.policy(self.obs[T])
+            self.values[T].copy_(v)
+        self._gae()
+
+    def _gae(self):
+        """GAE(lambda), as PPO2 computes it: adv[t] = delta[t] + gamma * lam * nonterminal[t] * adv[t + 1], with the deltas
+        of all steps computed at once."""
+        T = self.T
+        torch.sub(1.0, self.dones, out=self._nonterm)
+        torch.mul(self._nonterm, self.gamma * self.lam, out=self._coef)
+        torch.mul(self.values[1:], self._nonterm, out=self._delta)
+        self._delta.mul_(self.gamma).add_(self.rewards).sub_(self.values[:T])
+        self.adv[T - 1].copy_(self._delta[T - 1])
+        for t in range(T - 2, -1, -1):
+            torch.addcmul(self._delta[t], self._coef[t], self.adv[t + 1], out=self.adv[t])
         torch.add(self.adv, self.values[:T], out=self.returns)
 
     def collect(self):

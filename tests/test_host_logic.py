@@ -147,3 +147,39 @@ def test_history_rows_from_frames_host_code(align):
     assert np.array_equal(out.reshape(-1, 32), want)
     with pytest.raises(ValueError):
         _abi.check(L.shipsim_assemble_history(None, fr.ctypes.data, None, 1, N))
+
+
+def test_rollout_collector_fused_policy_and_gae_on_cpu():
+    """RolloutCollector runs the two trunks of MlpPolicy as one block-diagonal network (observation scale folded into
+    layer 1) and computes GAE from deltas of all steps at once: both agree with the plain formulation (train/
+    stable_baselines/ppo.py:88 MlpPolicy; PPO2's GAE recurrence).  Host logic only: no env, no device."""
+    torch = pytest.importorskip("torch")
+    from ship_sim_gym_b200.rollout import MlpPolicy, RolloutCollector
+    torch.manual_seed(0)
+    pol = MlpPolicy()
+    N, D, T, H, A = 257, 32, 9, 64, 3
+    c = RolloutCollector.__new__(RolloutCollector)               # the buffers _refresh_fused / _forward_fused touch, without an env
+    c.policy = pol
+    c._alloc_fused(N, D, H, A, T, dict(dtype=torch.float32))
+    c.obs = (torch.rand(T + 1, N, D) * 600.0)
+    with torch.no_grad():
+        c._refresh_fused()
+        for t in (0, T):
+            c._forward_fused(t)
+            logits, v = pol(c.obs[t])
+            assert torch.allclose(c._out[t, :, :A], logits, atol=2e-6) and torch.allclose(c._out[t, :, A], v, atol=2e-6)
+    # GAE: the vectorised deltas + one fused multiply-add per step against the textbook loop
+    g, lam = 0.99, 0.95
+    rew, val = torch.randn(T, N), torch.randn(T + 1, N)
+    done = (torch.rand(T, N) < 0.1).to(torch.uint8)
+    want, last = torch.empty(T, N), torch.zeros(N)
+    for t in range(T - 1, -1, -1):
+        nt = 1.0 - done[t].float()
+        last = rew[t] + g * val[t + 1] * nt - val[t] + g * lam * nt * last
+        want[t] = last
+    c.T, c.gamma, c.lam = T, g, lam
+    c.rewards, c.values, c.dones = rew, val, done
+    c._nonterm, c._coef, c._delta = torch.empty(T, N), torch.empty(T, N), torch.empty(T, N)
+    c.adv, c.returns = torch.empty(T, N), torch.empty(T, N)
+    c._gae()
+    assert torch.allclose(c.adv, want, atol=1e-5) and torch.allclose(c.returns, want + val[:T], atol=1e-5)
