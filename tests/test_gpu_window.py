@@ -153,6 +153,13 @@ def test_auto_selection():
     assert e2.launch_info()["steps_in_flight"] == 1
     with pytest.raises(ValueError):
         _env(16, bank, steps_in_flight=5)
+    # the window is as long as still lets every warp be resident (include/shipsim.h: SHIPSIM_WINDOW_AUTO_MAX_ENVS)
+    for n, want in ((2368, 32), (2369, 16), (4736, 16), (4737, 8), (32768, 8), (32769, 1)):
+        e3 = _env(n, bank)
+        e3.reset()
+        e3.rollout(None, K=32)
+        assert e3.launch_info()["steps_in_flight"] == want, (n, e3.launch_info())
+        e3.close()
 
 
 def test_million_envs_agree_with_small_shards():
