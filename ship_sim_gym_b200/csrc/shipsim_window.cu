@@ -22,9 +22,14 @@
 //      on average).
 // A warp holds E = 32/T envs; envs of a warp advance independently (each has its own step cursor k0).
 //
-// Shared-memory rings (per env, T+1 slots): observation frames and plane-phase rows.  Slot cb is the "carry": the
-// frame / planes of the last committed step (or of the reset), i.e. what step k0 starts from; slot cb+1+t belongs to
-// speculated step t.  Committing n steps just advances cb by n.
+// Shared memory per env: the plane-phase rows live in a ring of T+1 slots -- slot cb is the "carry", the planes of the
+// last committed step (or of the reset), i.e. what step k0's lidar looks at; slot cb+1+t belongs to speculated step t;
+// committing n steps just advances cb by n.  The observation frames sit in T+1 linear slots: slot 0 is the carry frame
+// (rewritten after every window by the lane of the last committed step), slot 1+t the frame of step t, so that the
+// copy-out addresses are compile-time offsets.
+//   1. uses a log2(T)-round prefix for the integer rudder recurrence (clamped additions compose), not a T-step chain;
+//   2. runs the separating-axis test per env group on the earliest undecided step and, with auto-reset, drops the steps
+//      behind the first done; lidar queries are cast for committed steps only.
 #include "shipsim_geom.cuh"
 #include "shipsim_launch.h"
 
@@ -53,7 +58,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
     __shared__ float2 s_goal[NW * E * kGoals];
     __shared__ float4 s_rf[NW * E * 2];         // reset frame, first two float4 (the rest is -1)
     __shared__ float4 s_ph[NW * 32 * 2];        // physics scan -> lanes: (th, w, bits(rudder), -) and (x, y, vx, vy) per step
-    __shared__ int4 s_env[NW * E];              // per env, for the copy-out: step cursor, committed steps, carry slot, reset?
+    __shared__ int4 s_env[NW * E];              // per env, for the copy-out: step cursor, committed steps, (carry slot of the plane ring), reset?
     __shared__ float s_ray[2 * 32];
     __shared__ unsigned s_src[NW][32];          // ray pass: compacted (plane row | frame offset) of the needy steps
     __shared__ float s_stat[NW][8];
@@ -150,7 +155,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
         // cpBodyUpdateVelocity -- the same operations in the same order as step_kernel, split so that as little as
         // possible is serial.  Every lane of the group runs the scans in lockstep (no divergence, no waiting); the
         // group's first lane drops each step's result into shared memory and lane t picks up step t.
-        float mx, my, mth, mvx, mvy, mw, mc, ms;
+        float mx, my, mth, mc, ms;
         int mrud;
         {
             float4 *ph = s_ph + (warp * 32 + gbase) * 2;
@@ -191,7 +196,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
             __syncwarp();
             {
                 const float2 v = *reinterpret_cast<const float2 *>(ph + 2 * t);
-                mth = v.x; mw = v.y; mrud = rud_t;
+                mth = v.x; mrud = rud_t;
             }
             sincos_fast(mth, ms, mc);                   // one sincos per lane instead of T per lane
             // thrust of step t acts along the heading the step STARTS from: the trig of step t-1 (or of the carry)
@@ -217,7 +222,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
             __syncwarp();
             {
                 const float4 v = ph[2 * t + 1];
-                mx = v.x; my = v.y; mvx = v.z; mvy = v.w;
+                mx = v.x; my = v.y;
             }
         }
 
