@@ -183,3 +183,42 @@ def test_rollout_collector_fused_policy_and_gae_on_cpu():
     c.adv, c.returns = torch.empty(T, N), torch.empty(T, N)
     c._gae()
     assert torch.allclose(c.adv, want, atol=1e-5) and torch.allclose(c.returns, want + val[:T], atol=1e-5)
+
+
+def test_clamped_additions_compose_like_the_window_kernel_assumes():
+    """window_kernel (shipsim_window.cu, scan 1a) gets the T rudder values of a window from a log2(T)-round prefix over
+    (a, lo, hi) triples instead of a T-step chain, relying on: clamp(clamp(r + a, lo, hi) + a', lo', hi') ==
+    clamp(r + a + a', max(lo + a', lo'), min(max(hi + a', lo'), hi')) with clamp(x, lo, hi) = min(max(x, lo), hi)
+    (Ship.rotate / clamp_rudder, models.py:136-146: rudder steps of 5 clamped to +-10).  Exhaustive over short
+    sequences, random over window-sized ones."""
+    import itertools
+    rng = np.random.RandomState(0)
+
+    def serial(r0, incs):
+        out, r = [], r0
+        for a in incs:
+            r = min(max(r + a, -10), 10)
+            out.append(r)
+        return out
+
+    def prefix(r0, incs):                      # Kogge-Stone, exactly as the kernel: lanes t >= off take lane t - off first
+        f = [(a, -10, 10) for a in incs]
+        off = 1
+        while off < len(f):
+            g = list(f)
+            for t in range(off, len(f)):
+                pa, plo, phi = f[t - off]
+                fa, flo, fhi = f[t]
+                g[t] = (pa + fa, max(plo + fa, flo), min(max(phi + fa, flo), fhi))
+            f, off = g, off * 2
+        return [min(max(r0 + a, lo), hi) for a, lo, hi in f]
+
+    for T in (1, 2, 3, 4):
+        for r0 in (-10, -5, 0, 5, 10):
+            for incs in itertools.product((-5, 0, 5), repeat=T):
+                assert serial(r0, incs) == prefix(r0, list(incs))
+    for T in (4, 8, 16, 32):
+        for _ in range(500):
+            r0 = int(rng.choice([-10, -5, 0, 5, 10]))
+            incs = [int(v) for v in rng.choice([-5, 0, 5], size=T)]
+            assert serial(r0, incs) == prefix(r0, incs)
