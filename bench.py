@@ -67,11 +67,12 @@ def load_peaks():
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons with NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._halt = threading.Event()
+        self._armed = False          # samples count only from arm() on (the thread starts before the barrier)
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -93,6 +94,9 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
         }
         while not self._halt.is_set():
+            if not self._armed:
+                time.sleep(0.0005)
+                continue
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -105,6 +109,12 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             time.sleep(self.period)
+
+    def arm(self):
+        self._armed = True
+
+    def armed_samples(self):
+        return len(self.samples)
 
     def stop(self):
         self._halt.set()
@@ -135,17 +145,103 @@ def cpu_port_rate(n_envs, budget_s, threads):
     return n_envs * K / dt, K, dt
 
 
+def probe_real_reference():
+    """is the real reference runnable here?  Needs pymunk < 6, pygame and gym importable and the
+    reference package `ship_gym` on the path (`baseline/_ref/`, a driver-written install; SHIPSIM_REF_PATH overrides it
+    for local experiments).  Returns (module dict, label) or (None, why-not)."""
+    for d in (os.environ.get("SHIPSIM_REF_PATH"), os.path.join(ROOT, "baseline", "_ref")):
+        if d and os.path.isdir(d) and d not in sys.path:
+            sys.path.insert(0, d)
+    os.environ.setdefault("SDL_VIDEODRIVER", "dummy")
+    try:
+        import pymunk
+        import pygame  # noqa: F401
+        import gym  # noqa: F401
+        ver = str(getattr(pymunk, "version", "0"))
+        if int(ver.split(".")[0]) >= 6:
+            return None, "pymunk %s is >= 6 (the reference mutates a Vec2d, ship_gym/models.py:146)" % ver
+        from ship_gym.config import EnvConfig, GameConfig
+        from ship_gym.ship_env import ShipEnv
+        return dict(ShipEnv=ShipEnv, GameConfig=GameConfig, EnvConfig=EnvConfig), "reference(pymunk %s)" % ver
+    except Exception as exc:        # ModuleNotFoundError in this image
+        return None, "%s: %s" % (type(exc).__name__, exc)
+
+
+def _real_env_worker(conn, mods_path, seconds, stub_render, fps, speed):
+    """One process = one reference ShipEnv (the SubprocVecEnv pattern of train/stable_baselines/ppo.py:122-123)."""
+    mods, _ = probe_real_reference()
+    gc, ec = mods["GameConfig"], mods["EnvConfig"]
+    gc.SPEED, gc.FPS, gc.DEBUG = speed, fps, False
+    env = mods["ShipEnv"](gc, ec)
+    if stub_render:
+        env.game.render = lambda *a, **k: None
+    env.reset()
+    n, t_end = 0, time.perf_counter() + 1.0
+    while time.perf_counter() < t_end:                       # 1 s warm-up
+        if env.step(env.action_space.sample())[2]:
+            env.reset()
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        if env.step(env.action_space.sample())[2]:
+            env.reset()
+        n += 1
+    conn.send((n, time.perf_counter() - t0))
+
+
+def real_reference_rates(seconds=10.0):
+    """BASELINE.md section 3 rows C2-C4 with the real reference: one env uncapped (FPS=100000, train/rllib/ppo.py:13),
+    the same with ShipGame.render stubbed, and one env per host core.  Only called when probe_real_reference succeeds."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+
+    def run(n_proc, stub):
+        pipes, procs = [], []
+        for _ in range(n_proc):
+            a, b = ctx.Pipe()
+            pr = ctx.Process(target=_real_env_worker, args=(b, None, seconds, stub, 100000, 10))
+            pr.start()
+            pipes.append(a)
+            procs.append(pr)
+        res = [c.recv() for c in pipes]
+        for pr in procs:
+            pr.join()
+        return sum(n / dt for n, dt in res)
+
+    cores = os.cpu_count() or 1
+    return {"C2_single_uncapped": run(1, False), "C3_single_render_stubbed": run(1, True), "C4_all_cores": run(cores, False),
+            "cores": cores}
+
+
 def run_reference_arm(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path.  The reference is Python over
-    pymunk/Chipmunk, which cannot be installed in this image, so this times the C restatement (kind "port"),
-    with every host thread, each step being a bounded sample of the workload."""
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores, rank 0 only.
+    When the real reference is importable (probe_real_reference) it is timed through its own public API, one ShipEnv per
+    core (kind "reference"); in this image it is not (pymunk / pygame / gym absent), and the arm times the float64 C
+    restatement in oracle/ (kind "port") with every host thread, on the WHOLE job's envs (ENVS x world), each step being
+    a bounded sample of the rollout."""
     if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    mods, label = probe_real_reference()
+    if mods is not None:
+        per = max(2.0, min(20.0, 60.0 / max(1, args.steps + args.warmup)))
+        rates = real_reference_rates(per)
+        value = rates["C4_all_cores"]
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "label": label,
+                             "sample": "one real ShipEnv per core, %.0f s each, FPS=100000, random actions" % per,
+                             "rows": rates},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+        }
+        emit(line)
         return
     import oracle
     from ship_sim_gym_b200 import ScenarioBank
-    cores = os.cpu_count() or 1
+    n_envs = ENVS * world                       # the whole job: what `global_envs` says
     bank = ScenarioBank.generate(N_SCENARIOS, (600, 600), seed=SEED).as_dict()
-    env = oracle.OracleEnv(ENVS, bank, auto_reset=True, seed=SEED, n_threads=cores)
+    env = oracle.OracleEnv(n_envs, bank, auto_reset=True, seed=SEED, n_threads=cores)
     env.reset()
     want = ("obs", "reward", "done")
     t0 = time.perf_counter()
@@ -159,18 +255,20 @@ def run_reference_arm(args, rank, world):
     for _ in range(args.steps):
         env.step(None, K=sample_K, want=want)
     dt = time.perf_counter() - t0
-    value = ENVS * sample_K * args.steps / dt
-    sample = "%d envs x %d env-steps per bench step (of %d), auto-reset, Philox random actions" % (ENVS, sample_K, ROLLOUT)
+    value = n_envs * sample_K * args.steps / dt
+    sample = "%d envs x %d env-steps per bench step (of %d), auto-reset, Philox random actions" % (n_envs, sample_K, ROLLOUT)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "label": "restated-reference (no pymunk in image: %s)" % label},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "reference = pure Python over pymunk/Chipmunk (not installable here); timed arm is the float64 C "
-                "restatement in oracle/ (faster than the real Python env: no cffi, no pygame, no clock.tick sleep)",
+        "note": "reference = pure Python over pymunk/Chipmunk (not installable here); timed arm is the un-optimised float64 C "
+                "restatement in oracle/ (it rebuilds the bank planes every step, but has no cffi, no pygame, no "
+                "clock.tick sleep: faster than the real Python env, i.e. a conservative baseline)",
     }
     emit(line)
 
@@ -185,6 +283,33 @@ def workload_config(world):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def oracle_self_check(env, actions, obs, rew, done, state0, rank, steps=64, n_check=512):
+    """The headline launch itself against the float64 oracle: the first `steps` steps of the K = ROLLOUT launch that
+    started from `state0`, for the first `n_check` envs (tests/parity.py tolerances: pose / lidar 1e-4 relative, reward
+    and done exact away from grazing decisions).  Raises on mismatch -- a fast kernel with different results is not a
+    result."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle
+    import parity
+    n = min(n_check, env.num_envs)
+    bank = env.bank.as_dict()
+    orc = oracle.OracleEnv(n, bank, auto_reset=True, seed=SEED, env_id_offset=rank * ENVS)
+    orc.reset()
+    st = [state0[k][:n] for k in ("pose", "ints", "lidar", "goals", "ep_return")]
+    parity.load_oracle_state(orc, st[0].astype(np.float64), st[1], st[2].astype(np.float64),
+                             st[3].reshape(n, 10).astype(np.float64), st[4].astype(np.float64))
+    a = actions[:steps, :n].cpu().numpy()
+    ref = orc.step(a)
+    rep = parity.compare_steps(ref, obs[:steps, :n].cpu().numpy(), rew[:steps, :n].cpu().numpy(),
+                               done[:steps, :n].cpu().numpy(), margin_thr=1e-3, label="bench self-check")
+    if rep["excluded_frac"] > 0.05:
+        raise AssertionError("bench self-check: %.3f of the env-steps excluded as grazing" % rep["excluded_frac"])
+    return {"env_steps_compared": rep["compared"], "of": rep["total"], "excluded_frac": rep["excluded_frac"],
+            "max_rel_err": rep["max_rel_err"], "checker": "oracle/ (float64 C restatement), first %d steps x %d envs of a "
+            "K=%d launch" % (steps, n, ROLLOUT)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -192,7 +317,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the extra (non-headline) configurations")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other (non-headline) configurations")
+    ap.add_argument("--no-self-check", action="store_true")
     ap.add_argument("--lanes", type=int, default=0)
     ap.add_argument("--window", type=int, default=0, help="steps_in_flight (0 = auto)")
     args = ap.parse_args()
@@ -220,29 +346,33 @@ def main():
     actions = torch.randint(0, 3, (ROLLOUT, ENVS), dtype=torch.int32, device=dev, generator=gen)
     out = env.alloc_rollout(ROLLOUT)
     reducer = sdist.StatsReducer(dev)
+    reduce_mode = os.environ.get("SHIPSIM_BENCH_REDUCE", "full")
 
     def one_step():
         env.rollout(actions, out=out)
-        if world > 1:       # one all-reduce of the episode statistics per rollout; it overlaps the next rollout's kernel
-            mode = os.environ.get("SHIPSIM_BENCH_REDUCE", "full")
-            if mode == "full":
-                env.stats_tensor(clear=True, out=reducer.next_buffer())
+        if world > 1:       # one all-reduce of the (cumulative) episode statistics per rollout; it overlaps the next rollout's kernel
+            if reduce_mode == "full":
+                env.stats_tensor(clear=False, out=reducer.next_buffer())
                 reducer.reduce()
-            elif mode == "local":
-                env.stats_tensor(clear=True)
+            elif reduce_mode == "local":
+                env.stats_tensor(clear=False)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        one_step()
-    barrier()
+    # NVML is initialised and the sampler thread started BEFORE the barrier (nvmlInit takes milliseconds, a different
+    # number in every process: done after the barrier it made the ranks enter the timed region milliseconds apart)
     sampler = ClockSampler(local)
     sampler.start()
-    l0 = env.launch_info()["launches"]
+    for _ in range(args.warmup):
+        one_step()
+    reducer.wait_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = env.launch_info()["launches"]
+    barrier()
+    sampler.arm()
     ev0.record()
     for _ in range(args.steps):
         one_step()
@@ -251,7 +381,7 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = env.launch_info()["launches"] - l0
-    if sampler.nv is not None and len(sampler.samples) < 5:       # region too short for NVML: extend, untimed
+    if sampler.nv is not None and sampler.armed_samples() < 5:    # region too short for NVML: extend, untimed
         t_end = time.time() + 0.5
         while time.time() < t_end:          # no collective in here: ranks run different numbers of these
             env.rollout(actions, out=out)
@@ -264,18 +394,48 @@ def main():
     env_steps = float(ENVS) * ROLLOUT * args.steps * world
     value = env_steps / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (the fused step kernel is the only kernel in the timed region)
+    # ---- the only collective of the path, checked on the GPUs: the all-reduced vector of the last rollout must equal
+    # the sum of the all-gathered per-rank vectors; the printed statistics are the GLOBAL ones
+    local_stats = env.stats_tensor(clear=False).clone()
+    collective = None
+    if world > 1 and reduce_mode == "full":
+        reduced = reducer.latest().clone()
+        torch.cuda.synchronize()
+        ok, err, mat = sdist.verify_all_reduce(local_stats, reduced)
+        collective = {"op": "all_reduce(SUM) f64[16] per rollout, NCCL", "verified": ok, "max_rel_err": err,
+                      "ranks_seen": int(mat.shape[0]), "per_rank_episodes": [float(x) for x in mat[:, 0].tolist()],
+                      "reducer_depth": len(reducer.bufs)}
+        if not ok:
+            raise AssertionError("statistics all-reduce differs from the sum of the per-rank vectors: %r" % collective)
+        global_stats = reduced
+    else:
+        global_stats = local_stats
+    stats = dict(zip(sdist_names(), [float(x) for x in global_stats.tolist()]))
+    stats["steps"] = float(ENVS) * ROLLOUT * (args.steps + args.warmup) * world
+    stats["scope"] = "global (all ranks)" if world > 1 else "single rank"
+
+    # ---- roofline of the dominant kernel (the fused step kernel is the only kernel of ours in the timed region)
     peak, peak_src = load_peaks()
     launch_ms = ms / args.steps
     achieved = b_alg(ROLLOUT) * ENVS * ROLLOUT / (launch_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), "profiles/traffic.json <- " + str(tj.get("source", "ncu --set full capture"))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernel": kernel_name(env.launch_info()), "bytes_per_env_step": b_alg(ROLLOUT),
-                "launch_ms": launch_ms}
+                "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_name(env.launch_info()),
+                "bytes_per_env_step": b_alg(ROLLOUT), "launch_ms": launch_ms}
+
+    # ---- the headline launch against the oracle (rank 0; after the timed region)
+    self_check = None
+    if rank == 0 and not args.no_self_check:
+        torch.cuda.synchronize()
+        state0 = env.get_state()
+        env.rollout(actions, out=out)
+        torch.cuda.synchronize()
+        self_check = oracle_self_check(env, actions, out[0], out[1], out[2], state0, rank)
 
     # ---- end to end through the C ABI with HOST buffers (copies inside the timed region)
     e2e = None
@@ -298,27 +458,37 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     h2d_b, d2h_b = env.host_traffic()
     e2e = {"value": float(ENVS) * ROLLOUT * e2e_steps * world / float(t.item()), "unit": UNIT,
-           # counted by shipsim_step_host from the copies it issues.  HISTORY_SIZE = 2: only frames cross PCIe (64 B per
-           # env-step) and the 128-byte [previous | current] rows are rebuilt in the caller's buffer by host threads
+           # counted by shipsim_step_host from the copies it issues
            "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
            "host_obs_bytes_per_step": int(h_obs.numel() * 4),
-           "steps": e2e_steps, "api": "BatchedShipEnv.step_host -> shipsim_step_host (pinned host buffers)"}
+           "steps": e2e_steps, "api": "BatchedShipEnv.step_host -> shipsim_step_host (pinned host buffers)",
+           "host_threads": env.host_threads()}
 
-    # ---- extra configurations (not the headline; same kernel)
+    # ---- other BASELINE configurations (not the headline; same kernels)
     extra = {}
     if not args.no_extra:
         extra = extra_configs(torch, dev, rank, world)
+        roofline["other_configs"] = {k: {kk: v[kk] for kk in v if kk in ("env_steps_per_s", "launch_ms", "K", "roofline_frac",
+                                                                        "roofline_frac_per_gpu", "kernel", "rollout_ms")}
+                                     for k, v in extra.items()}
 
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
+            mods, label = probe_real_reference()
             v_all, K_all, dt_all = cpu_port_rate(ENVS, 10.0, cores)
             v_one, K_one, dt_one = cpu_port_rate(ENVS, 5.0, 1)
             cpu = {"value": v_all, "unit": UNIT, "cores": cores, "kind": "port",
+                   "label": "restated-reference (%s)" % label,
                    "sample": "%d envs x %d env-steps (%.1f s), all host threads; single thread: %.3g env-steps/s "
                              "(%d env-steps, %.1f s)" % (ENVS, K_all, dt_all, v_one, K_one, dt_one),
                    "single_thread_value": v_one}
+            if mods is not None:            # BASELINE.md section 3 rows C2-C4 with the real thing
+                rates = real_reference_rates(10.0)
+                cpu.update({"value": rates["C4_all_cores"], "kind": "reference", "label": label, "rows": rates,
+                            "port_value": v_all,
+                            "sample": "one real ShipEnv per core (SubprocVecEnv pattern), 10 s each, FPS=100000"})
         info = env.launch_info()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -326,7 +496,7 @@ def main():
             "data": "synthetic", "config": workload_config(world), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks,
             "launch_shape": {k: info[k] for k in ("lanes_per_env", "threads_per_cta", "ctas", "steps_in_flight")},
-            "stats": env.stats(), "extra": extra,
+            "stats": stats, "collective": collective, "self_check": self_check, "extra": extra,
         }
         emit(line)
     if world > 1:
@@ -334,9 +504,16 @@ def main():
         dist.destroy_process_group()
 
 
+def sdist_names():
+    from ship_sim_gym_b200 import _abi
+    return _abi.STAT_NAMES
+
+
 def extra_configs(torch, dev, rank, world):
-    """Other BASELINE.json configurations, timed with the same kernel (reported under "extra", never as the
-    headline): configs[2] hard map 65,536 envs; configs[3] 1,048,576 envs sharded over the ranks."""
+    """Other BASELINE.json configurations, timed with the same kernels (reported under "extra" and
+    roofline.other_configs, never as the headline): configs[1] stepped gym-style (K = 1, a policy in the loop cannot
+    hand over 1,000 actions up front); configs[2] hard map 65,536 envs; configs[3] 1,048,576 envs sharded over the
+    ranks; configs[4] policy + 16,384 envs."""
     import torch.distributed as dist
     from ship_sim_gym_b200 import BatchedShipEnv, ScenarioBank, dist as sdist
     from ship_sim_gym_b200.config import EnvConfig, GameConfig
@@ -346,22 +523,24 @@ def extra_configs(torch, dev, rank, world):
     def timed(env, K, reps, with_allreduce):
         acts = torch.randint(0, 3, (K, env.num_envs), dtype=torch.int32, device=dev)
         out = env.alloc_rollout(K)
-        stats = torch.zeros(16, dtype=torch.float64, device=dev)
+        reducer = sdist.StatsReducer(dev)
 
         def go():
             env.rollout(acts, out=out)
-            if with_allreduce and world > 1:
-                stats.copy_(env.stats_tensor(clear=True))
-                sdist.all_reduce_stats(stats)
+            if with_allreduce and world > 1:    # asynchronous: the reduction of rollout i overlaps rollout i + 1
+                env.stats_tensor(clear=False, out=reducer.next_buffer())
+                reducer.reduce()
         for _ in range(3):
             go()
+        reducer.wait_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
             go()
+        reducer.wait_all()
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -370,35 +549,45 @@ def extra_configs(torch, dev, rank, world):
         ms = float(t.item()) / reps
         return ms
 
-    # configs[2]: builder-defined "max difficulty" map: 1000x1000, N=30, width_frac=0.9, 180 deg fan
+    bank = ScenarioBank.generate(N_SCENARIOS, (600, 600), seed=SEED)
     if rank == 0:
+        # configs[1] as a gym caller sees it: one launch per env-step (the serial-in-time kernel; B_alg(1) = 325 B)
+        env = BatchedShipEnv(ENVS, bank=bank, seed=SEED, device=dev, validate_actions=False)
+        env.reset()
+        ms = _single_rank_timed(torch, dev, env, 1, 200)
+        rate = ENVS / (ms * 1e-3)
+        res["default_4096_K1"] = {"env_steps_per_s": rate, "launch_ms": ms, "K": 1, "kernel": kernel_name(env.launch_info()),
+                                  "roofline_frac": rate * b_alg(1) / 1e9 / peak}
+        env.close()
+        del env
+        # configs[2]: builder-defined "max difficulty" map: 1000x1000, N=30, width_frac=0.9, 180 deg fan
         class GC(GameConfig):
             BOUNDS = (1000, 1000)
-        bank = ScenarioBank.generate(256, (1000, 1000), seed=SEED, map_N=30, width_frac=0.9)
-        env = BatchedShipEnv(65536, GC, EnvConfig, bank=bank, seed=SEED, honour_lidar_config=True, device=dev, validate_actions=False)
+        hbank = ScenarioBank.generate(256, (1000, 1000), seed=SEED, map_N=30, width_frac=0.9)
+        env = BatchedShipEnv(65536, GC, EnvConfig, bank=hbank, seed=SEED, honour_lidar_config=True, device=dev, validate_actions=False)
         env.reset()
         K = 100
         ms = _single_rank_timed(torch, dev, env, K, 10)
         rate = 65536 * K / (ms * 1e-3)
-        res["hard_map_65536"] = {"env_steps_per_s": rate, "launch_ms": ms, "K": K,
+        res["hard_map_65536"] = {"env_steps_per_s": rate, "launch_ms": ms, "K": K, "kernel": kernel_name(env.launch_info()),
                                  "roofline_frac": rate * b_alg(K) / 1e9 / peak}
         env.close()
         del env
     # configs[3]: 1,048,576 envs sharded over the ranks, 128-step rollouts, one stats all-reduce per rollout
     total = 1048576
     off, cnt = sdist.shard(total, rank, world)
-    bank = ScenarioBank.generate(N_SCENARIOS, (600, 600), seed=SEED)
     env = BatchedShipEnv(cnt, bank=bank, seed=SEED, device=dev, env_id_offset=off, validate_actions=False)
     env.reset()
     K = 128 if world > 1 else 32       # one GPU: 1M envs x 128 steps of obs would be 17 GB; keep it modest
     ms = timed(env, K, 5, True)
     rate = total * K / (ms * 1e-3)
     res["sharded_1048576"] = {"env_steps_per_s": rate, "launch_ms": ms, "K": K, "envs_per_gpu": cnt,
+                              "kernel": kernel_name(env.launch_info()),
                               "roofline_frac_per_gpu": rate / world * b_alg(K) / 1e9 / peak}
     # K=1 gym-style stepping of the same batch (one launch per env-step)
     ms1 = timed(env, 1, 50, False)
     rate1 = total / (ms1 * 1e-3)
-    res["sharded_1048576_K1"] = {"env_steps_per_s": rate1, "launch_ms": ms1, "K": 1,
+    res["sharded_1048576_K1"] = {"env_steps_per_s": rate1, "launch_ms": ms1, "K": 1, "kernel": kernel_name(env.launch_info()),
                                  "roofline_frac_per_gpu": rate1 / world * b_alg(1) / 1e9 / peak}
     env.close()
     # configs[4]: MLP policy + 16,384 envs on the same GPU, 128-step rollouts replayed from ONE CUDA graph: no host

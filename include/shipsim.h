@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SHIPSIM_ABI_VERSION 2
+#define SHIPSIM_ABI_VERSION 3
 #define SHIPSIM_N_GOALS 5        /* game.py:17  N_GOALS */
 #define SHIPSIM_N_BEAMS 10       /* models.py:29 LiDAR(n_beams=10): the only beam count the reference ever uses */
 #define SHIPSIM_FRAME 16         /* ship_env.py:43 n_states = 2+1+1+2+n_beams */
@@ -99,7 +99,9 @@ typedef struct shipsim_config {
                                     of different steps run on different lanes; the window is cut at the first `done`).
                                     0 = choose from num_envs, 1 = off (one step after another), else 4, 8, 16 or 32.
                                     Results are bit-identical either way.                              */
-    int32_t reserved0;           /* keeps sizeof a multiple of 8; must be 0                           */
+    int32_t host_threads;        /* shipsim_step_host: host threads that rebuild the observation rows (the caller included).
+                                    0 = min(16, hardware threads); with several ranks on one box pass
+                                    hardware threads / ranks so that the ranks do not oversubscribe the cores  */
 } shipsim_config;
 
 /* num_envs up to which steps_in_flight = 0 selects the time-parallel kernel (measured on B200, profiles/) */
@@ -205,6 +207,8 @@ int shipsim_launch_count(const shipsim_t *h, int64_t *out);
 int shipsim_launch_shape(const shipsim_t *h, int32_t *lanes_per_env, int32_t *threads_per_cta, int32_t *ctas);
 /* bytes the last shipsim_step_host moved over PCIe (host->device actions; device->host frames / rows, rewards, dones) */
 int shipsim_host_traffic(const shipsim_t *h, int64_t *h2d_bytes, int64_t *d2h_bytes);
+/* host threads shipsim_step_host uses to rebuild observation rows (0 until its first call creates the pool) */
+int shipsim_host_threads(const shipsim_t *h, int32_t *n_threads);
 /* steps of one env the last launch speculated together (1 = the serial-in-time kernel ran) */
 int shipsim_launch_window(const shipsim_t *h, int32_t *steps_in_flight);
 

@@ -29,8 +29,10 @@ import sys
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, os.path.join(HERE, "shims"))
-sys.path.insert(0, "/root/reference")
+if "pymunk" not in sys.modules:      # oracle/live_check.py imports the REAL pymunk first; everyone else gets the shim
+    sys.path.insert(0, os.path.join(HERE, "shims"))
+if not any(os.path.isdir(os.path.join(p, "ship_gym")) for p in sys.path if p):
+    sys.path.insert(0, os.environ.get("SHIPSIM_REF_PATH", "/root/reference"))
 
 from ship_gym import game_map  # noqa: E402  (the real reference)
 from ship_gym.config import EnvConfig, GameConfig  # noqa: E402
@@ -142,9 +144,8 @@ def scenario_pin(seed, W, H):
             "goals": np.array([[go.x, go.y] for go in game.goals])}
 
 
-def main():
-    out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
-    os.makedirs(out_dir, exist_ok=True)
+def all_episodes():
+    """The recorded episodes, in fixture order (also what oracle/live_check.py replays against the real pymunk)."""
     episodes = []
     # default config (config.py:14-24): BOUNDS 600x600, SPEED 10, HISTORY 2
     for seed in range(6):
@@ -170,6 +171,17 @@ def main():
     # builder-defined "max difficulty" map: N=30, width_frac=0.9, 1000x1000
     for seed, kind in ((60, "thrusty"), (61, "left1"), (62, "right"), (63, "random"), (64, "straight")):
         episodes.append(run_episode(seed, kind, W=1000, H=1000, speed=10, T=150, map_N=30, map_wf=0.9))
+    return episodes
+
+
+def main():
+    if "--live" in sys.argv:             # diff the committed fixtures against the real pymunk instead of regenerating
+        import live_check
+        live_check.run()
+        return
+    out_dir = os.path.join(os.path.dirname(HERE), "tests", "golden")
+    os.makedirs(out_dir, exist_ok=True)
+    episodes = all_episodes()
 
     flat = {}
     for i, rec in enumerate(episodes):

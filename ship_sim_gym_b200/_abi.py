@@ -21,7 +21,7 @@ SYMBOLS = (
     "shipsim_load_scenarios", "shipsim_state_bytes", "shipsim_stats_bytes", "shipsim_bind_state", "shipsim_reset",
     "shipsim_step", "shipsim_step_host", "shipsim_stats_read", "shipsim_set_state", "shipsim_get_state",
     "shipsim_launch_count", "shipsim_launch_shape", "shipsim_launch_window", "shipsim_set_max_steps",
-    "shipsim_generate_scenarios", "shipsim_read_scenarios", "shipsim_render", "shipsim_assemble_history", "shipsim_host_traffic",
+    "shipsim_generate_scenarios", "shipsim_read_scenarios", "shipsim_render", "shipsim_assemble_history", "shipsim_host_traffic", "shipsim_host_threads",
 )
 
 
@@ -37,7 +37,7 @@ class Config(C.Structure):
         ("max_steps", C.c_int32), ("history", C.c_int32), ("auto_reset", C.c_int32), ("lidar_beams", C.c_int32),
         ("lidar_spread_deg", C.c_float), ("lidar_distance", C.c_float), ("ship_w", C.c_float), ("ship_h", C.c_float),
         ("mass", C.c_float), ("thrust", C.c_float), ("goal_radius", C.c_float), ("step_penalty", C.c_float),
-        ("spawn_y", C.c_float), ("lanes_per_env", C.c_int32), ("steps_in_flight", C.c_int32), ("reserved0", C.c_int32),
+        ("spawn_y", C.c_float), ("lanes_per_env", C.c_int32), ("steps_in_flight", C.c_int32), ("host_threads", C.c_int32),
     ]
 
 
@@ -79,6 +79,7 @@ def load():
     L.shipsim_render.argtypes = [vp, i32, i32, i32, vp, vp]
     L.shipsim_assemble_history.argtypes = [vp, vp, vp, i64, i64]
     L.shipsim_host_traffic.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    L.shipsim_host_threads.argtypes = [vp, C.POINTER(i32)]
     L.shipsim_launch_count.argtypes = [vp, C.POINTER(i64)]
     L.shipsim_launch_shape.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.shipsim_launch_window.argtypes = [vp, C.POINTER(i32)]

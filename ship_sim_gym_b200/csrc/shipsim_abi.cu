@@ -85,6 +85,7 @@ struct shipsim_handle {
     double *d_gen_xy = nullptr, *d_gen_goals = nullptr;   // raw output of the device scenario generator (for read-back)
     int *d_gen_n = nullptr;
     int gen_count = 0;
+    float ship_reach = 0.f;                  // bound on the distance of any hull point from the lidar origin
     int lanes = 1;
     int window = 1;                          // steps of one env speculated together (1 = the serial-in-time kernel)
     // staging for shipsim_step_host (allocated on first use, sized for the largest K seen)
@@ -149,7 +150,7 @@ extern "C" int shipsim_config_default(shipsim_config *c)
     c->goal_radius = 5.f; c->step_penalty = -0.01f; c->spawn_y = 25.f;   // game.py:82, ship_env.py:13, game.py:274
     c->lanes_per_env = 0;
     c->steps_in_flight = 0;
-    c->reserved0 = 0;
+    c->host_threads = 0;
     return SHIPSIM_OK;
 }
 
@@ -224,6 +225,7 @@ static int derive_params(shipsim_handle *h)
     double rmax = 0;
     for (auto &v : hull) rmax = std::max(rmax, std::sqrt(v.x * v.x + v.y * v.y));
     p.goal_cull_r2 = (float)((rmax + c.goal_radius) * (rmax + c.goal_radius) * 1.0001);
+    h->ship_reach = (float)(2.0 * rmax);
     p.acc_dt = (float)((double)c.thrust / c.mass * c.dt);
     p.ang_dt = (float)((double)c.thrust / moment * c.dt);
     // lidar fan (models.py:48-49,62)
@@ -251,6 +253,7 @@ extern "C" int shipsim_create(const shipsim_config *cfg, int device, shipsim_t *
     if (cfg->struct_size != (int32_t)sizeof(shipsim_config)) return fail(SHIPSIM_ERR_ARG, "shipsim_config size mismatch (ABI version?)");
     if (cfg->num_envs < 1) return fail(SHIPSIM_ERR_ARG, "num_envs must be >= 1");
     if (cfg->history < 1) return fail(SHIPSIM_ERR_ARG, "history_size must be greater than zero");   // ship_env.py:46-47
+    if (cfg->host_threads < 0) return fail(SHIPSIM_ERR_ARG, "host_threads must be >= 0");
     if (cfg->history > 2) return fail(SHIPSIM_ERR_UNSUPPORTED, "history > 2 is assembled by the host layer from 1-frame observations");
     if (cfg->lidar_beams != SHIPSIM_N_BEAMS) return fail(SHIPSIM_ERR_UNSUPPORTED, "lidar_beams must be 10");
     if (!(cfg->dt > 0.f) || !(cfg->bounds_w > 0.f) || !(cfg->bounds_h > 0.f) || !(cfg->lidar_distance > 0.f) || cfg->max_steps < 1
@@ -394,7 +397,9 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
         const double pad = -(double)h->p.gridp.x0;
         const double cw = ((double)h->cfg.bounds_w + 2.0 * pad) / kGridN, ch = ((double)h->cfg.bounds_h + 2.0 * pad) / kGridN;
         const double margin = 0.05 + 1e-4 * std::max((double)h->cfg.bounds_w, (double)h->cfg.bounds_h);
-        const double reach = std::max((double)h->cfg.lidar_distance, std::sqrt(cw * cw + ch * ch)) + margin;
+        // the cell is looked up at the LIDAR ORIGIN, and its masks also decide "bank not near => no ship-vs-bank test":
+        // the reach must cover the hull as seen from that origin (every hull point lies within 2 * max |hull vertex|)
+        const double reach = std::max({(double)h->cfg.lidar_distance, (double)h->ship_reach, std::sqrt(cw * cw + ch * ch)}) + margin;
         e = launch_build_grid(dxy, dn, n_scen, dev_maxv, (double)h->p.gridp.x0, (double)h->p.gridp.y0, cw, ch, reach, margin, dg, 0);
     }
     if (e == cudaSuccess) {
@@ -409,8 +414,14 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
     cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_spawn);
     h->d_bank = d; h->d_edges = de; h->d_grid = dg; h->d_spawn = dsp;
     h->p.bank = d; h->p.edges_d = de; h->p.grid = dg; h->p.spawn_rows = dsp;
+    const int old_n = h->p.n_scen;
     h->p.n_scen = n_scen; h->p.maxv = dev_maxv; h->p.scen_stride4 = stride4; h->p.hull_max = dev_maxv;
     h->launches += 2;
+    if (h->p.state && n_scen < old_n) {      // live envs may hold ids of the old, larger bank
+        CU(launch_clamp_scenarios(h->p.state, h->cfg.num_envs, n_scen, 0));
+        CU(cudaDeviceSynchronize());
+        h->launches++;
+    }
     return SHIPSIM_OK;
 }
 
@@ -447,7 +458,9 @@ extern "C" int shipsim_generate_scenarios(shipsim_t *h, int32_t n_scen, uint64_t
         const double pad = -(double)h->p.gridp.x0;
         const double cw = ((double)h->cfg.bounds_w + 2.0 * pad) / kGridN, ch = ((double)h->cfg.bounds_h + 2.0 * pad) / kGridN;
         const double margin = 0.05 + 1e-4 * std::max((double)h->cfg.bounds_w, (double)h->cfg.bounds_h);
-        const double reach = std::max((double)h->cfg.lidar_distance, std::sqrt(cw * cw + ch * ch)) + margin;
+        // the cell is looked up at the LIDAR ORIGIN, and its masks also decide "bank not near => no ship-vs-bank test":
+        // the reach must cover the hull as seen from that origin (every hull point lies within 2 * max |hull vertex|)
+        const double reach = std::max({(double)h->cfg.lidar_distance, (double)h->ship_reach, std::sqrt(cw * cw + ch * ch)}) + margin;
         e = launch_build_grid(dxy, dn, n_scen, kMaxHull, (double)h->p.gridp.x0, (double)h->p.gridp.y0, cw, ch, reach, margin, dg, s);
     }
     int hull_max = 0;
@@ -466,8 +479,14 @@ extern "C" int shipsim_generate_scenarios(shipsim_t *h, int32_t n_scen, uint64_t
     h->d_bank = d; h->d_edges = de; h->d_grid = dg; h->d_spawn = dsp;
     h->d_gen_xy = dxy; h->d_gen_goals = dgo; h->d_gen_n = dn; h->gen_count = n_scen;
     h->p.bank = d; h->p.edges_d = de; h->p.grid = dg; h->p.spawn_rows = dsp;
+    const int old_n = h->p.n_scen;
     h->p.n_scen = n_scen; h->p.maxv = maxv; h->p.scen_stride4 = stride4; h->p.hull_max = hull_max;
     h->launches += 5;
+    if (h->p.state && n_scen < old_n) {
+        CU(launch_clamp_scenarios(h->p.state, h->cfg.num_envs, n_scen, s));
+        CU(cudaStreamSynchronize(s));
+        h->launches++;
+    }
     return SHIPSIM_OK;
 }
 
@@ -601,6 +620,7 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
         if (!h->d_frame0) CU(cudaMalloc(&h->d_frame0, N * kFrame * sizeof(float)));
         if (!h->pool) {
             int nt = std::max(1, std::min(16, (int)std::thread::hardware_concurrency()));
+            if (h->cfg.host_threads > 0) nt = std::min(h->cfg.host_threads, 256);
             if (const char *ev = std::getenv("SHIPSIM_HOST_THREADS")) nt = std::max(1, atoi(ev));
             h->pool = new HostPool(nt - 1);
         }
@@ -673,6 +693,13 @@ extern "C" int shipsim_host_traffic(const shipsim_t *h, int64_t *h2d_bytes, int6
     if (!h) return fail(SHIPSIM_ERR_ARG, "NULL argument");
     if (h2d_bytes) *h2d_bytes = h->last_h2d;
     if (d2h_bytes) *d2h_bytes = h->last_d2h;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_host_threads(const shipsim_t *h, int32_t *n_threads)
+{
+    if (!h || !n_threads) return fail(SHIPSIM_ERR_ARG, "NULL argument");
+    *n_threads = h->pool ? h->pool->size() : 0;
     return SHIPSIM_OK;
 }
 

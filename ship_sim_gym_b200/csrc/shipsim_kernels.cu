@@ -565,7 +565,8 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
     float4 l0, l1, l2, g0, g1, g2;
     load_env(p, e, r, l0, l1, l2, g0, g1, g2);
     const int ep = first ? 0 : r.episode + 1;
-    const int scen = scenario ? scenario[e] : pick_scenario(p, p.env_id_offset + e, ep);
+    int scen = scenario ? scenario[e] : pick_scenario(p, p.env_id_offset + e, ep);
+    scen = min(max(scen, 0), p.n_scen - 1);       // caller-supplied ids index the bank: never out of range (the host layer raises first)
     reset_env(p, r, scen, ep);
     const float4 *rec = p.bank + (size_t)scen * p.scen_stride4;
     g0 = __ldg(rec + 2); g1 = __ldg(rec + 3); g2 = __ldg(rec + 4);
@@ -585,6 +586,18 @@ __global__ void __launch_bounds__(256) reset_kernel(const __grid_constant__ Step
         o[2] = neg;
         o[3] = neg;
     }
+}
+
+// After a bank swap (shipsim_load_scenarios / shipsim_generate_scenarios on a live handle) a stored scenario id may
+// exceed the new bank: fold it into range so that no kernel indexes bank / grid / edges_d / spawn_rows out of bounds.
+// (The env keeps its old goals until its next reset; the host layer resets the whole batch after a swap.)
+__global__ void __launch_bounds__(256) clamp_scenarios_kernel(float4 *state, int N, int n_scen)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    float4 *q = state + (size_t)4 * N + e;
+    const int scen = __float_as_int(q->z);
+    if (scen < 0 || scen >= n_scen) q->z = __int_as_float((int)((unsigned)scen % (unsigned)n_scen));
 }
 
 // the observation frame of the CURRENT state of every env (ShipEnv.__add_states, ship_env.py:79-113): what the next
@@ -663,6 +676,12 @@ cudaError_t launch_reset(const StepParams &p, const uint8_t *mask, const int *sc
 {
     const int threads = 256;
     reset_kernel<<<(p.N + threads - 1) / threads, threads, 0, stream>>>(p, mask, scenario, first, obs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_clamp_scenarios(float4 *state, int N, int n_scen, cudaStream_t stream)
+{
+    clamp_scenarios_kernel<<<(N + 255) / 256, 256, 0, stream>>>(state, N, n_scen);
     return cudaGetLastError();
 }
 

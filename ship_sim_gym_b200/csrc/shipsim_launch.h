@@ -24,6 +24,7 @@ cudaError_t launch_gen_scenarios(unsigned long long seed, int n_scen, double W, 
 cudaError_t launch_pack_bank(double *hull_xy, const int *hull_n, const double *goals, int n_scen, int maxv, int stride4, float4 *bank,
                              EdgeD *edges, cudaStream_t stream);
 cudaError_t launch_max_hull(const int *hull_n, int n, int *out, cudaStream_t stream);
+cudaError_t launch_clamp_scenarios(float4 *state, int N, int n_scen, cudaStream_t stream);
 cudaError_t launch_frame(const StepParams &p, float4 *out, cudaStream_t stream);
 cudaError_t launch_render(const StepParams &p, int e, int img_w, int img_h, uint8_t *rgb, cudaStream_t stream);
 cudaError_t launch_stats_reduce(double *slots, double *out, int clear, cudaStream_t stream);

@@ -85,14 +85,17 @@ class BatchedShipEnv(object):
 
     def __init__(self, num_envs, game_config=None, env_config=None, device=None, seed=0, n_scenarios=1024,
                  bank=None, map_N=10, map_width_frac=0.5, auto_reset=True, honour_lidar_config=False,
-                 env_id_offset=0, lanes_per_env=0, validate_actions=True, scenario_source="host", steps_in_flight=0):
+                 env_id_offset=0, lanes_per_env=0, validate_actions=True, scenario_source="host", steps_in_flight=0,
+                 host_threads=0):
         self.knobs = snapshot(game_config, env_config, honour_lidar_config)
         if self.knobs["lidar"]["N_BEAMS"] != _abi.N_BEAMS:
             raise NotImplementedError("N_BEAMS must be 10")
         self.num_envs = int(num_envs)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.device = torch.device("cuda") if device is None else torch.device(device)
         if self.device.type != "cuda":
             raise _abi.ShipsimError("BatchedShipEnv needs a CUDA device: there is no CPU fallback")
+        if self.device.index is None:          # 'cuda' = the CURRENT device, not device 0: handle and buffers must agree
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.L = _abi.load()
         self._needs_reset = True
         self.action_space = Discrete(3)                        # ship_env.py:19
@@ -121,9 +124,18 @@ class BatchedShipEnv(object):
         cfg.lidar_distance = self.knobs["lidar"]["DISTANCE"]
         cfg.lanes_per_env = int(lanes_per_env)
         cfg.steps_in_flight = int(steps_in_flight)     # 0 auto, 1 serial-in-time kernel, 4/8/16/32 time-parallel window
+        if not host_threads:
+            # step_host's row-assembly pool: the box's cores are shared by the ranks torchrun started on it
+            import os
+            ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+            host_threads = max(1, min(16, (os.cpu_count() or 1) // ranks_here))
+        cfg.host_threads = int(host_threads)
         self.cfg = cfg
+        self.reset_epoch = 0
+        self.last_reset_obs = None
+        self.params_epoch = 0                  # bumped whenever kernel parameters change (captured CUDA graphs go stale)
         self._h = C.c_void_p()
-        _abi.check(self.L.shipsim_create(C.byref(cfg), self.device.index or 0, C.byref(self._h)))
+        _abi.check(self.L.shipsim_create(C.byref(cfg), self.device.index, C.byref(self._h)))
         self._obs_dim_kernel = _abi.FRAME * cfg.history
 
         self._n_generated = 0
@@ -146,6 +158,7 @@ class BatchedShipEnv(object):
             _abi.check(self.L.shipsim_bind_state(self._h, self.state.data_ptr(), self._stats_slots.data_ptr(), self._stream()))
         self._hist = None
         self.total_steps = 0
+        self._state_bound = True
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -163,12 +176,19 @@ class BatchedShipEnv(object):
             pass
 
     def load_scenarios(self, bank):
-        """Upload a ScenarioBank (curriculum changes call this between rollouts)."""
+        """Upload a ScenarioBank (curriculum changes call this between rollouts).  On a live batch every env is then
+        RESET: its stored scenario id and goals belong to the old bank (ShipGame.reset builds level and goals together,
+        game.py:271-272); `last_reset_obs` holds the reset observations."""
         if tuple(bank.bounds) != tuple(self.bounds):
             raise ValueError("scenario bank was generated for bounds %s, env has %s" % (bank.bounds, self.bounds))
         self.bank = bank
-        _abi.check(self.L.shipsim_load_scenarios(self._h, bank.hull_xy.ctypes.data, bank.hull_n.ctypes.data,
-                                                 bank.goals.ctypes.data, len(bank), bank.maxv))
+        self._n_scen = len(bank)
+        with torch.cuda.device(self.device):
+            _abi.check(self.L.shipsim_load_scenarios(self._h, bank.hull_xy.ctypes.data, bank.hull_n.ctypes.data,
+                                                     bank.goals.ctypes.data, len(bank), bank.maxv))
+        self.params_epoch = getattr(self, "params_epoch", 0) + 1
+        if getattr(self, "_state_bound", False) and not self._needs_reset:
+            self.reset()
 
     def _gen_count(self):
         return self._n_generated
@@ -182,6 +202,8 @@ class BatchedShipEnv(object):
                                                          float(map_width_frac), self._stream()))
         self.bank = None
         self._n_generated = int(n_scenarios)
+        self._n_scen = int(n_scenarios)
+        self.params_epoch = getattr(self, "params_epoch", 0) + 1
         self._needs_reset = True
 
     def read_scenarios(self):
@@ -198,6 +220,7 @@ class BatchedShipEnv(object):
         """Change EnvConfig.MAX_STEPS (config.py:16) of the live batch -- a curriculum knob."""
         _abi.check(self.L.shipsim_set_max_steps(self._h, int(max_steps)))
         self.knobs["max_steps"] = int(max_steps)
+        self.params_epoch += 1
 
     def seed(self, seed=None):
         """ship_env.py:52-60 seeds numpy only; here it also re-keys the action-space sampler."""
@@ -233,11 +256,19 @@ class BatchedShipEnv(object):
         obs = torch.zeros(N, self._obs_dim_kernel, dtype=torch.float32, device=self.device)
         m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
         sc = None if scenario is None else torch.as_tensor(scenario, device=self.device).to(torch.int32).contiguous()
+        if sc is not None:
+            if sc.numel() != N:
+                raise ValueError("scenario must hold one id per env")
+            lo, hi = int(sc.min()), int(sc.max())
+            if lo < 0 or hi >= self._n_scen:
+                raise ValueError("scenario ids must be in [0, %d), got [%d, %d]" % (self._n_scen, lo, hi))
         first = 1 if (mask is None and self._needs_reset) else 0
         with torch.cuda.device(self.device):
             _abi.check(self.L.shipsim_reset(self._h, None if m is None else m.data_ptr(), None if sc is None else sc.data_ptr(),
                                             first, obs.data_ptr(), self._stream()))
         self._needs_reset = False
+        self.reset_epoch += 1
+        self.last_reset_obs = obs if mask is None else None
         if self.history > 2:
             frame = obs
             if self._hist is None or mask is None:
@@ -332,6 +363,12 @@ class BatchedShipEnv(object):
             _abi.check(self.L.shipsim_step_host(self._h, a.ctypes.data, K, ptr(obs), ptr(rew), ptr(done), self._stream()))
         self.total_steps += K * self.num_envs
         return obs, rew, done
+
+    def host_threads(self):
+        """Host threads step_host() uses to rebuild observation rows (0 before its first call)."""
+        n = C.c_int32()
+        _abi.check(self.L.shipsim_host_threads(self._h, C.byref(n)))
+        return n.value
 
     def host_traffic(self):
         """(host->device, device->host) bytes the last step_host() moved over PCIe."""

@@ -56,13 +56,12 @@ class RolloutCollector(object):
         self.returns = torch.empty(T, N, **f32)
         self.use_graph = bool(use_graph)
         self._graph = None
+        self._graph_epoch = -1
         self._fused = isinstance(policy, MlpPolicy)
         if self._fused:
             lin = [policy.pi[0], policy.pi[2], policy.pi[4], policy.vf[0], policy.vf[2], policy.vf[4]]
             H, A = lin[0].out_features, lin[2].out_features
             assert lin[0].in_features == D and lin[3].out_features == H and lin[5].out_features == 1
-            self._H, self._A = H, A
-            self._W1, self._b1 = torch.empty(D, 2 * H, **f32), torch.empty(2 * H, **f32)
             self._alloc_fused(N, D, H, A, T, f32)
             self._z = torch.empty(N, A, **f32)
         self._noise = torch.empty(T, N, policy.pi[4].out_features if self._fused else 3, **f32)
@@ -71,6 +70,7 @@ class RolloutCollector(object):
         self._delta = torch.empty(T, N, **f32)
         env.validate_actions = False                            # the range check would need a host sync per step
         self.obs[0].copy_(env.reset())
+        self._seen_reset_epoch = env.reset_epoch
 
     def _alloc_fused(self, N, D, H, A, T, f32):
         self._H, self._A = H, A
@@ -140,11 +140,23 @@ class RolloutCollector(object):
         torch.add(self.adv, self.values[:T], out=self.returns)
 
     def collect(self):
-        """One rollout; the buffers (obs, actions, logp, values, rewards, dones, adv, returns) hold the result."""
+        """One rollout; the buffers (obs, actions, logp, values, rewards, dones, adv, returns) hold the result.
+        The captured graph freezes the kernel parameters (StepParams travels by value: episode cap, scenario-bank
+        pointers, ...), so it is dropped and captured again whenever the env's `params_epoch` has moved -- after
+        set_max_steps / load_scenarios / generate_scenarios, e.g. from a CurriculumDriver between rollouts."""
+        if self._seen_reset_epoch != self.env.reset_epoch:
+            # the batch was reset behind the collector's back (a bank swap resets every env): go on from that observation
+            if self.env.last_reset_obs is not None:
+                self.obs[0].copy_(self.env.last_reset_obs)
+            self._seen_reset_epoch = self.env.reset_epoch
         if not self.use_graph:
             self._collect()
         else:
+            if self._graph is not None and self._graph_epoch != self.env.params_epoch:
+                self._graph = None
             if self._graph is None:
+                self._graph_epoch = self.env.params_epoch
+                steps_before = self.env.total_steps
                 s = torch.cuda.Stream(device=self.env.device)
                 s.wait_stream(torch.cuda.current_stream(self.env.device))
                 with torch.cuda.stream(s):
@@ -155,8 +167,11 @@ class RolloutCollector(object):
                 with torch.cuda.graph(self._graph):
                     self._collect()
                     self.obs[0].copy_(self.obs[self.T])         # next rollout continues where this one ended
-                return self                                     # the capture pass does not execute; replay below next call
+                # the capture pass enqueued nothing: only the warm-up rollout ran
+                self.env.total_steps = steps_before + self.T * self.env.num_envs
+                return self
             self._graph.replay()
+            self.env.total_steps += self.T * self.env.num_envs
             return self
         self.obs[0].copy_(self.obs[self.T])
         return self
