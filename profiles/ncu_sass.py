@@ -11,10 +11,10 @@ kname = rows[0][1]
 hdr = rows[1]
 ci, si, ti = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Thread Instructions Executed")
 sass = [(r[1].strip(), float(r[ci] or 0), float(r[si] or 0), float(r[ti] or 0)) for r in rows[2:] if len(r) == len(hdr)]
-m = re.search(r"step_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>", kname)
-mangled = "_ZN7shipsim11step_kernelILi%sELi%sELi%sEEEvNS_10StepParamsE" % (m.group(1), m.group(2), m.group(3))
+m = re.search(r"step_kernel<([^>]*)>", kname)
+mangled = ("_ZN7shipsim11step_kernelI" + "".join("Li%sE" % v for v in re.findall(r"\(int\)(\d+)", m.group(1))) + "EEvNS_10StepParamsE") if m else None
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "ship_sim_gym_b200", "libshipsim.so")], cwd=tmp, capture_output=True)
+subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("SHIPSIM_LIB") or os.path.join(ROOT, "ship_sim_gym_b200", "libshipsim.so")], cwd=tmp, capture_output=True)
 cub = [f for f in glob.glob(os.path.join(tmp, "*.cubin")) if os.path.basename(f).startswith("shipsim_kernels")][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout.splitlines()
 lines, inside, cur = [], False, ("?", 0)

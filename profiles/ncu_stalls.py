@@ -11,15 +11,15 @@ hdr = rows[1]
 col = {h: i for i, h in enumerate(hdr)}
 reasons = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 data = [r for r in rows[2:] if len(r) == len(hdr)]
-m = re.search(r"step_kernel<\(int\)(\d+), \(int\)(\d+), \(int\)(\d+)>", kname)
-mangled = "_ZN7shipsim11step_kernelILi%sELi%sELi%sEEEvNS_10StepParamsE" % (m.group(1), m.group(2), m.group(3)) if m else None
+m = re.search(r"step_kernel<([^>]*)>", kname)
+mangled = ("_ZN7shipsim11step_kernelI" + "".join("Li%sE" % v for v in re.findall(r"\(int\)(\d+)", m.group(1))) + "EEvNS_10StepParamsE") if m else None
 cubin_prefix = "shipsim_kernels"
 mw = re.search(r"window_kernel<\(int\)(\d+), \(int\)(\d+)>", kname)
 if mw:
     mangled = "_ZN7shipsim13window_kernelILi%sELi%sEEEvNS_10StepParamsE" % (mw.group(1), mw.group(2))
     cubin_prefix = "shipsim_window"
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("SHIPSIM_LIB") or os.path.join(ROOT, "ship_sim_gym_b200", "libshipsim.so")], cwd=tmp, capture_output=True)
+subprocess.run(["cuobjdump", "-xelf", "all", os.environ.get("SHIPSIM_LIB") or os.environ.get("SHIPSIM_LIB") or os.path.join(ROOT, "ship_sim_gym_b200", "libshipsim.so")], cwd=tmp, capture_output=True)
 cub = [f for f in glob.glob(os.path.join(tmp, "*.cubin")) if os.path.basename(f).startswith(cubin_prefix)][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", cub], capture_output=True, text=True).stdout.splitlines()
 lines, inside, cur = [], False, ("?", 0)

@@ -360,7 +360,7 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
                 const double ex = bx - ax, ey = by - ay, ln = std::sqrt(ex * ex + ey * ey);
                 if (!(ln > 0)) return fail(SHIPSIM_ERR_ARG, "degenerate hull edge");
                 E[i] = make_float4((float)(ey / ln), (float)(-ex / ln), (float)bx, (float)by);   // cpvrperp: outward for CCW
-                ED[i].nx = ey / ln; ED[i].ny = -ex / ln; ED[i].vx = (float)bx; ED[i].vy = (float)by; ED[i].len = (float)ln;
+                ED[i].set_normal(ey / ln, -ex / ln); ED[i].vx = (float)bx; ED[i].vy = (float)by; ED[i].len = (float)ln;
                 { const int self = b * kMaxHull + i; std::memcpy(&ED[i].pad, &self, 4); }
             }
         }
@@ -385,7 +385,7 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
     cudaError_t e = cudaMalloc(&d, host.size() * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&de, edges.size() * sizeof(EdgeD));
     if (e == cudaSuccess) e = cudaMalloc(&dg, grid_cells * sizeof(uint4));
-    if (e == cudaSuccess) e = cudaMalloc(&dsp, (size_t)n_scen * (1 + 2 * 4) * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&dsp, (size_t)n_scen * (1 + 2 * 4) * sizeof(float4)   /* kScr4, shipsim_geom.cuh */);
     if (e == cudaSuccess) e = cudaMalloc(&dxy, rxy.size() * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&dn, (size_t)n_scen * 2 * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(d, host.data(), host.size() * sizeof(float4), cudaMemcpyHostToDevice);
@@ -444,7 +444,7 @@ extern "C" int shipsim_generate_scenarios(shipsim_t *h, int32_t n_scen, uint64_t
     cudaError_t e = cudaMalloc(&d, (size_t)n_scen * stride4 * sizeof(float4));
     if (e == cudaSuccess) e = cudaMalloc(&de, (size_t)n_scen * 2 * kMaxHull * sizeof(EdgeD));
     if (e == cudaSuccess) e = cudaMalloc(&dg, (size_t)n_scen * kGridN * kGridN * sizeof(uint4));
-    if (e == cudaSuccess) e = cudaMalloc(&dsp, (size_t)n_scen * (1 + 2 * 4) * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&dsp, (size_t)n_scen * (1 + 2 * 4) * sizeof(float4)   /* kScr4, shipsim_geom.cuh */);
     if (e == cudaSuccess) e = cudaMalloc(&dxy, (size_t)n_scen * 2 * kMaxHull * 2 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&dgo, (size_t)n_scen * 10 * sizeof(double));
     if (e == cudaSuccess) e = cudaMalloc(&dn, (size_t)n_scen * 2 * sizeof(int));

@@ -29,15 +29,25 @@ constexpr int kMaxHull = 32;        // SHIPSIM_MAX_HULL: fixed stride of the dou
 constexpr int kGridN = 32;          // the reach grid has kGridN x kGridN cells per scenario
 constexpr unsigned kFull = 0xffffffffu;
 
-// Double-precision plane of one bank edge, used only for LIVE ray/edge pairs (32 bytes = two 16-byte loads).
-// A lidar reading is d / (-n.dir): an error of d is amplified by 1/cos(incidence), and an fp32 normal (6e-8 rad)
-// swings d by 6e-5 over a 1000-unit edge, so live edges use the double plane the reference's cpSplittingPlane
-// holds.  Built on the host from the SAME fp32-rounded vertices the fp32 records carry.
+// Plane of one bank edge as the lidar and the plane phase see it (32 bytes = two 16-byte loads).  A lidar reading is
+// d / (-n.dir): an error of d is amplified by 1/cos(incidence), and an fp32 normal (6e-8 rad) swings d by 6e-5 over a
+// 1000-unit edge, so the unit normal is kept to 48 bits as an unevaluated sum of two floats (hi + lo, "double-float"):
+// n.q then costs two fp32 FMAs per term instead of a trip through the FP64 pipe and six conversions.  (Round 1 stored the
+// normal as doubles; the double evaluation held ~24 registers at its peak, which is what made the warp-cooperative
+// plane phase spill at 96 registers -- and spills are ruinous in a kernel whose L1 is almost all shared memory.)
+// Built from the SAME fp32-rounded vertices the fp32 records carry.
 struct EdgeD {
-    double nx, ny;                  // outward unit normal of the edge v_{i-1} -> v_i
+    float nxh, nyh;                 // outward unit normal of the edge v_{i-1} -> v_i, leading parts
+    float nxl, nyl;                 // ... and what is left of the double value: n = (nxh + nxl, nyh + nyl)
     float vx, vy;                   // v_i
     float len;                      // |v_i - v_{i-1}|
-    float pad;                      // bits: the record's own index, bank * kMaxHull + i (it travels with staged copies)
+    float pad;                      // bits: the record's own index, bank * kMaxHull + i
+
+    __host__ __device__ void set_normal(double nx, double ny)
+    {
+        nxh = (float)nx; nxl = (float)(nx - (double)nxh);
+        nyh = (float)ny; nyl = (float)(ny - (double)nyh);
+    }
 };
 
 // Reach grid: one uint4 per cell.  x / y: bit i set <=> edge i of bank 0 / 1 comes within max(lidar length, cell
@@ -60,7 +70,7 @@ struct GridParams {
 struct StepParams {
     float4 *state;               // [kPlanes][N]
     const float4 *bank;          // packed scenario records
-    const EdgeD *edges_d;        // [n_scen][2][kMaxHull] double planes
+    const EdgeD *edges_d;        // [n_scen][2][kMaxHull] two-float planes
     const uint4 *grid;           // [n_scen][kGridN*kGridN] reach grid
     const float4 *spawn_rows;    // [n_scen][1 + 2*kMaxCand] plane-phase output at the spawn pose
     GridParams gridp;

@@ -1,5 +1,5 @@
 // shipsim_geom.cuh -- geometry pieces shared by the step kernels (serial-in-time step_kernel and the time-parallel
-// window_kernel): action fetch, hull AABB, reach-grid lookup, double-precision plane evaluation, ray-vs-plane test,
+// window_kernel): action fetch, hull AABB, reach-grid lookup, two-float plane evaluation, ray-vs-plane test,
 // the plane phase and the serial ray query.  Both kernels call exactly these functions on the same inputs, which is
 // what makes their results bit-identical (tests/test_gpu_window.py).
 #pragma once
@@ -14,6 +14,17 @@ __device__ __forceinline__ int load_action(const StepParams &p, const char *ap, 
         case 0: return __ldg(reinterpret_cast<const int *>(ap));
         case 1: return (int)__ldg(reinterpret_cast<const long long *>(ap));
         case 2: return (int)__ldg(reinterpret_cast<const unsigned char *>(ap));
+        default: return random_action(p, gid, p.step0 + (unsigned)k);
+    }
+}
+
+// actions[k][e] by row index: the base pointer stays in the constant bank (no per-lane pointer to keep or spill)
+__device__ __forceinline__ int load_action_at(const StepParams &p, size_t idx, int k, long long gid)
+{
+    switch (p.action_dtype) {
+        case 0: return __ldg(reinterpret_cast<const int *>(p.actions) + idx);
+        case 1: return (int)__ldg(reinterpret_cast<const long long *>(p.actions) + idx);
+        case 2: return (int)__ldg(reinterpret_cast<const unsigned char *>(p.actions) + idx);
         default: return random_action(p, gid, p.step0 + (unsigned)k);
     }
 }
@@ -55,25 +66,26 @@ __device__ __forceinline__ uint4 load_cell(const StepParams &p, int scen, float 
     return __ldg(p.grid + ((size_t)scen * kGridN + iy) * kGridN + ix);
 }
 
-// A candidate plane seen from the ray origin (ox, oy) = (x + hx, y + hy), evaluated in double from the plane the
-// reference's cpSplittingPlane holds: d = n.(o - v_i), ta = cross(n, o - v_i).
+// A candidate plane seen from the ray origin (ox, oy) = (x + hx, y + hy): d = n.(o - v_i), ta = cross(n, o - v_i), with
+// the two-float normal of the record.  The difference o - v_i is formed in fp32 from fp32 inputs (exact when the two are
+// within a factor of two of each other, otherwise good to 1e-5 at map scale -- below what the fp32 pose itself carries).
 struct PlaneEval { float d, ta, nx, ny, len; };
 
-__device__ __forceinline__ PlaneEval eval_plane_rec(const double2 nd, const float4 ev, double xd, double yd, double hxd, double hyd)
+__device__ __forceinline__ PlaneEval eval_plane_rec(const float4 nn, const float4 ev, float x, float y, float hx, float hy)
 {
-    const double qx = (xd - (double)ev.x) + hxd, qy = (yd - (double)ev.y) + hyd;     // origin - v_i
+    const float qx = (x - ev.x) + hx, qy = (y - ev.y) + hy;                           // origin - v_i
     PlaneEval o;
-    o.d = (float)(nd.x * qx + nd.y * qy);
-    o.ta = (float)(nd.x * qy - nd.y * qx);
-    o.nx = (float)nd.x;
-    o.ny = (float)nd.y;
+    o.d = fmaf(nn.x, qx, __fmul_rn(nn.y, qy)) + fmaf(nn.z, qx, __fmul_rn(nn.w, qy));
+    o.ta = fmaf(nn.x, qy, -__fmul_rn(nn.y, qx)) + fmaf(nn.z, qy, -__fmul_rn(nn.w, qx));
+    o.nx = nn.x;
+    o.ny = nn.y;
     o.len = ev.z;
     return o;
 }
 
-__device__ __forceinline__ PlaneEval eval_plane(const EdgeD *E, double xd, double yd, double hxd, double hyd)
+__device__ __forceinline__ PlaneEval eval_plane(const EdgeD *E, float x, float y, float hx, float hy)
 {
-    return eval_plane_rec(__ldg(reinterpret_cast<const double2 *>(E)), __ldg(reinterpret_cast<const float4 *>(E) + 1), xd, yd, hxd, hyd);
+    return eval_plane_rec(__ldg(reinterpret_cast<const float4 *>(E)), __ldg(reinterpret_cast<const float4 *>(E) + 1), x, y, hx, hy);
 }
 
 __device__ __forceinline__ float rcp_approx(float x)
@@ -97,25 +109,63 @@ __device__ __forceinline__ bool ray_vs_plane(float d, float ta, float nxl, float
     return d >= 0.f && denom > 0.f && d <= denom && tang >= -len && tang <= 0.f;
 }
 
-constexpr int kMaxCand = 4;                  // candidate planes a scratch row holds (more -> serial path)
+constexpr int kMaxCand = 4;                  // candidate planes a scratch row holds (more -> serial ray query)
 constexpr int kScr4 = 1 + 2 * kMaxCand;      // scratch row: header + two float4 per plane (odd stride: conflict-free)
+constexpr int kRowPlane0 = 1;                // row index of the first plane
 // header.z bits
 constexpr int kHdrIn0 = 1 << 8, kHdrIn1 = 1 << 9, kHdrBig = 1 << 10;
+
+// One candidate plane at one pose (x, y, c, s; hx, hy = half extents of the hull's AABB): what the lidar of the next step
+// and the ship-vs-bank pre-test of this step need from it.
+struct PlaneOut { float d, ta, nxl, nyl, len; bool out, sep, keep; };
+
+template <bool WITH_SAT>
+__device__ __forceinline__ PlaneOut plane_at_pose(const StepParams &p, const float4 nn, const float4 ev, float x, float y, float hx,
+                                                  float hy, float c, float s)
+{
+    const float L = p.lidar_len;
+    const PlaneEval pe = eval_plane_rec(nn, ev, x, y, hx, hy);
+    PlaneOut o;
+    o.d = pe.d; o.ta = pe.ta; o.nxl = -L * pe.nx; o.nyl = -L * pe.ny; o.len = pe.len;
+    o.out = pe.d > 0.f;
+    // the normal in the body frame, where both the hull and the ray fan are constant
+    const float bnx = pe.nx * c + pe.ny * s, bny = pe.ny * c - pe.nx * s;
+    o.sep = false;
+    if (WITH_SAT) {
+        // does this bank plane have the whole ship in front of it?  n.(hull vertex j - v_i) = d - n.h + (R^T n).l_j
+        // (vertex 0 is the body origin)
+        float m = 0.f;
+#pragma unroll
+        for (int j = 1; j < kShipVerts; ++j) m = fminf(m, bnx * p.ship_lx[j] + bny * p.ship_ly[j]);
+        o.sep = pe.d - (pe.nx * hx + pe.ny * hy) + m > 0.f;
+    }
+    // Can any ray of the fan reach this plane at all?  A ray hits only if 0 <= d <= -L n.dir (ray_vs_plane), and over
+    // the fan -n.dir <= cos(max(0, angle(-n, fan axis) - half spread)).  Planes that fail (with a margin far above
+    // fp32 rounding) are left out of the row: fewer planes per ray, and often no ray pass for the env at all.
+    const float cm = -(bnx * p.fan_cx + bny * p.fan_cy);
+    float reach = 1.f;
+    if (cm < p.fan_cos) reach = cm * p.fan_cos + sqrt_approx(fmaxf(1.f - cm * cm, 0.f)) * p.fan_sin;    // a bound: approx is plenty
+    o.keep = pe.d >= 0.f && pe.d <= L * reach * 1.0001f + 1.0e-3f;
+    return o;
+}
 
 // Plane phase for one env at pose (x, y, c, s): fills the env's scratch row for the next lidar query and returns,
 // when WITH_SAT, bit b set <=> bank b is near and none of its candidate planes has the whole ship in front of it
 // (=> the full separating-axis pass has to decide).  Scratch row:
 //   [0]      c, s, bits(n | in0<<8 | in1<<9 | big<<10), 0
 //   [1+2i]   d, ta, -L*nx, -L*ny        [2+2i]  len, bank (0.f / 1.f), 0, 0
-//   big row (more than kMaxCand candidates; rays are then cast serially by the owner lane):
+//   big row (more than kMaxCand planes would have to be kept; rays are then cast serially by the owner lane):
 //   [1]      x, y, hx, hy               [2]     bits(scen), bits(m0), bits(m1), bits(flags)
-// STAGED: the raw EdgeD record of candidate i has already been copied (cp.async) into raw[2i], raw[2i+1]; the
-// record carries its own index (bank * kMaxHull + edge) in `pad`, so the candidate masks need not be walked again
-// (only cells with at most kMaxCand candidates are staged).
+// STAGED: the raw record of candidate i has already been copied (cp.async) into raw[2i], raw[2i+1]; the record carries
+// its own index (bank * kMaxHull + edge) in `pad`, so the candidate masks need not be walked again (only cells with at
+// most kMaxCand candidates are staged).
 // A cell may name more than kMaxCand candidates (long banks of short edges: the hard map): all of them are evaluated
 // -- the separating-plane pre-test and the inside test want every one -- and since the fan-reach cull drops about half,
 // the row usually still holds what the rays can reach.  Only when a (kMaxCand+1)-th plane would have to be kept does
-// the env fall back to the big row (serial ray query by the owner lane).
+// the env fall back to the big row.
+// (Round 2 also tried this phase warp-cooperatively -- the (env, candidate) pairs of a whole warp laid out by a prefix
+// sum and evaluated one per lane: 7-12 % fewer instructions, but longer dependent chains and more live registers; it
+// measured 1 % faster at 1M envs and 4 % slower on the two latency-bound shapes.  profiles/r02_b_coop_plane_phase.md.)
 template <bool WITH_SAT, bool STAGED>
 __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, float y, float hx, float hy, float c, float s, int scen,
                                                 const uint4 cell, float4 *row, const float4 *raw = nullptr)
@@ -123,64 +173,45 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
     unsigned m0 = cell.x, m1 = cell.y;
     const unsigned near = ((m0 != 0u || (cell.z & 1u)) ? 1u : 0u) | ((m1 != 0u || (cell.z & 2u)) ? 2u : 0u);
     const int ncand = (int)((cell.z >> 8) & 0xffu);
-    const float L = p.lidar_len;
     const EdgeD *E = p.edges_d + (size_t)scen * (2 * kMaxHull);
-    const double xd = (double)x, yd = (double)y, hxd = (double)hx, hyd = (double)hy;
     unsigned outm = 0u, sepm = 0u;
     int nk = 0;                                  // planes kept for the ray pass
-    double2 nd_next = make_double2(0.0, 0.0);
-    float4 ev_next = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 nn_next = make_float4(0.f, 0.f, 0.f, 0.f), ev_next = nn_next;
     if (!STAGED && ncand > 0) {
         int idx;
         if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
-        nd_next = __ldg(reinterpret_cast<const double2 *>(E + idx));
+        nn_next = __ldg(reinterpret_cast<const float4 *>(E + idx));
         ev_next = __ldg(reinterpret_cast<const float4 *>(E + idx) + 1);
     }
 #pragma unroll 1
     for (int n = 0; n < ncand; ++n) {
-        double2 nd;
-        float4 ev;
+        float4 nn, ev;
         if (STAGED) {
-            nd = *reinterpret_cast<const double2 *>(raw + 2 * n);
+            nn = raw[2 * n];
             ev = raw[2 * n + 1];
         } else {                                 // the next record is asked for before this one is evaluated
-            nd = nd_next; ev = ev_next;
+            nn = nn_next; ev = ev_next;
             if (n + 1 < ncand) {
                 int idx;
                 if (m0) { idx = __ffs(m0) - 1; m0 &= m0 - 1u; } else { idx = kMaxHull + __ffs(m1) - 1; m1 &= m1 - 1u; }
-                nd_next = __ldg(reinterpret_cast<const double2 *>(E + idx));
+                nn_next = __ldg(reinterpret_cast<const float4 *>(E + idx));
                 ev_next = __ldg(reinterpret_cast<const float4 *>(E + idx) + 1);
             }
         }
         const bool bank1 = __float_as_int(ev.w) >= kMaxHull;
         const unsigned bbit = bank1 ? 2u : 1u;
-        const PlaneEval pe = eval_plane_rec(nd, ev, xd, yd, hxd, hyd);
-        if (pe.d > 0.f) outm |= bbit;
-        // the normal in the body frame, where both the hull and the ray fan are constant
-        const float bnx = pe.nx * c + pe.ny * s, bny = pe.ny * c - pe.nx * s;
-        if (WITH_SAT) {
-            // does this bank plane have the whole ship in front of it?  n.(hull vertex j - v_i) = d - n.h + (R^T n).l_j
-            // (vertex 0 is the body origin)
-            float m = 0.f;
-#pragma unroll
-            for (int j = 1; j < kShipVerts; ++j) m = fminf(m, bnx * p.ship_lx[j] + bny * p.ship_ly[j]);
-            if (pe.d - (pe.nx * hx + pe.ny * hy) + m > 0.f) sepm |= bbit;
-        }
-        // Can any ray of the fan reach this plane at all?  A ray hits only if 0 <= d <= -L n.dir (ray_vs_plane), and over
-        // the fan -n.dir <= cos(max(0, angle(-n, fan axis) - half spread)).  Planes that fail (with a margin far above
-        // fp32 rounding) are left out of the row: fewer planes per ray, and often no ray pass for the env at all.
-        const float cm = -(bnx * p.fan_cx + bny * p.fan_cy);
-        float reach = 1.f;
-        if (cm < p.fan_cos) reach = cm * p.fan_cos + sqrt_approx(fmaxf(1.f - cm * cm, 0.f)) * p.fan_sin;    // a bound: approx is plenty
-        if (pe.d >= 0.f && pe.d <= L * reach * 1.0001f + 1.0e-3f) {
+        const PlaneOut o = plane_at_pose<WITH_SAT>(p, nn, ev, x, y, hx, hy, c, s);
+        if (o.out) outm |= bbit;
+        if (o.sep) sepm |= bbit;
+        if (o.keep) {
             if (!STAGED && nk == kMaxCand) {     // the row is full: big row (the masks are the cell's, not the walked ones)
                 row[0] = make_float4(c, s, __int_as_float(kHdrBig), 0.f);
                 row[1] = make_float4(x, y, hx, hy);
                 row[2] = make_float4(__int_as_float(scen), __uint_as_float(cell.x), __uint_as_float(cell.y), __uint_as_float(cell.z));
                 return near & ~sepm;            // what has been proven separated stays proven
             }
-            row[1 + 2 * nk] = make_float4(pe.d, pe.ta, -L * pe.nx, -L * pe.ny);
-            row[2 + 2 * nk] = make_float4(pe.len, bank1 ? 1.f : 0.f, 0.f, 0.f);
+            row[kRowPlane0 + 2 * nk] = make_float4(o.d, o.ta, o.nxl, o.nyl);
+            row[kRowPlane0 + 1 + 2 * nk] = make_float4(o.len, bank1 ? 1.f : 0.f, 0.f, 0.f);
             ++nk;
         }
     }
@@ -208,14 +239,13 @@ static __device__ __noinline__ void ray_query_serial(const StepParams &p, const 
     const unsigned masks[2] = {__float_as_uint(b4.y), __float_as_uint(b4.z)};
     const unsigned flags = __float_as_uint(b4.w);
     const EdgeD *E = p.edges_d + (size_t)scen * (2 * kMaxHull);
-    const double xd = (double)a.x, yd = (double)a.y, hxd = (double)a.z, hyd = (double)a.w;
     unsigned pend = (1u << kBeams) - 1u;
     for (int b = 0; b < 2; ++b) {
         bool out = false;
         unsigned hitm = 0u;
         float v[kBeams];
         for (unsigned m = masks[b]; m; m &= m - 1u) {
-            const PlaneEval pe = eval_plane(E + b * kMaxHull + (__ffs(m) - 1), xd, yd, hxd, hyd);
+            const PlaneEval pe = eval_plane(E + b * kMaxHull + (__ffs(m) - 1), a.x, a.y, a.z, a.w);
             out = out || (pe.d > 0.f);
 #pragma unroll
             for (int j = 0; j < kBeams; ++j) {

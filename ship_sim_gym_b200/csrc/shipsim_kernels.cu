@@ -17,67 +17,87 @@
 #ifndef SHIPSIM_MIN_BLOCKS
 #define SHIPSIM_MIN_BLOCKS 4
 #endif
+// Grids that fill the machine (one lane per env, >= 1,184 CTAs of 128 envs' worth): CTA size and CTAs per SM to aim
+// for.  Registers per thread follow from the pair: 128 x 5 -> 96, 64 x 9 -> 112, 128 x 4 / 64 x 8 -> 128.  Spills are
+// ruinous here (the L1 that would catch them is almost entirely carved out as shared memory), so the shape is chosen
+// as the most warps per SM that still compile without any.
+#ifndef SHIPSIM_BIG_THREADS
+#define SHIPSIM_BIG_THREADS 128
+#endif
+#ifndef SHIPSIM_BIG_MIN_BLOCKS
+#define SHIPSIM_BIG_MIN_BLOCKS 5
+#endif
 
 namespace shipsim {
 
+constexpr float kDeadGoal = 3.0e19f;        // coordinate of a goal that has been taken: its squared distance is +inf
+
 // MINB = CTAs per SM the register allocation aims for: 5 (96 registers) pays off only when the grid is large enough
 // to fill them, otherwise 4 (128 registers, less rematerialisation).
-template <int G, int HIST, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_constant__ StepParams p)
+//
+// Shared memory: ONE array; every env has one block of EB4 float4 (odd stride: the 128-bit accesses of a warp's envs
+// are conflict-free) holding its observation tile row, its plane row and its goals at compile-time offsets, addressed
+// from a single per-lane byte offset.  (Round 1 kept seven arrays with their own index arithmetic; at 96 registers the
+// compiler rebuilt those indices from threadIdx / blockIdx inside the loop: 12 % of the instructions, and an S2R
+// stall that was the hottest sample of the kernel.  The offsets are laundered through an empty asm so that they stay
+// in their registers.)
+template <int G, int HIST, int MINB, int THREADS>
+__global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_constant__ StepParams p)
 {
     constexpr int EPW = 32 / G;                 // envs per warp
     constexpr int OBS4 = 4 * HIST;              // float4 per obs row
     // ray pass: two passes (six envs) per loop trip in the 128-register build (grids that do not fill the machine are
     // latency bound: +4 % on the hard map at 65,536 envs); the 96-register build has no room for it (-1 % at 1M envs)
-    constexpr int kRayPassUnroll = MINB <= 4 ? 2 : 1;
-    constexpr int ROW4 = OBS4 + 1;              // padded tile row (odd float4 stride: conflict-free 128-bit accesses)
-    constexpr int CF = 16 * (HIST - 1);         // float offset of the newest frame inside a row
-    constexpr int NW = kThreads / 32;
-    __shared__ float4 s_tile[NW * EPW * ROW4];  // [older frame | newest frame] of every env; lidar slots = sticky vals
-    __shared__ float4 s_scr[NW * EPW * kScr4];  // plane-phase output of every env
-    __shared__ float2 s_goal[NW * kGoals * EPW];    // goal centres, [warp][goal][env]: only rewritten on reset
+    constexpr int kRayPassUnroll = MINB * THREADS <= 512 ? 2 : 1;
+    constexpr int CF = 16 * (HIST - 1);         // float offset of the newest frame inside the tile row
+    constexpr int NW = THREADS / 32;
+    // env block: [0, OBS4) tile row = [older frame | newest frame] (lidar slots = the sticky readings);
+    // [SCR, SCR + kScr4) plane row; [GOL, GOL + 3) goals (taken goals hold kDeadGoal)
+    constexpr int SCR = OBS4, GOL = OBS4 + kScr4;
+    // [RAW, RAW + 2 * kMaxCand): raw candidate-plane records (cp.async targets) -- only with G > 1 (few envs per CTA),
+    // where they are requested at the top of the iteration; with G = 1 that would cost 16 KB, so they land in the plane
+    // row itself once the ray pass has finished with it
+    constexpr int RAW = GOL + 3;
+    constexpr int EB4 = (RAW + (G > 1 ? 2 * kMaxCand : 0)) | 1;
+    constexpr int WX4 = EPW * EB4;              // warp block: the env blocks, then 2 float4 of ray-pass list, 2 of statistics
+    constexpr int WB4 = WX4 + 4;
+    __shared__ float4 smem[NW * WB4];
     __shared__ float s_ray[2 * 32];
-    __shared__ unsigned char s_src[NW][32];        // ray pass: compacted list of needy envs per warp
-    // Raw candidate-plane records (cp.async targets).  With G > 1 (few envs per CTA) they get their own area and are
-    // requested at the top of the iteration; with G = 1 that would cost 16 KB, so they land in the scratch row itself
-    // once the ray pass has finished with it.
-    constexpr int RAW4 = G > 1 ? NW * EPW * 2 * kMaxCand : 1;
-    __shared__ float4 s_raw[RAW4];
-    __shared__ float s_stat[NW][8];
+    char *const sm = reinterpret_cast<char *>(smem);
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // Everything a lane needs to find its data -- lane, warp, shared-memory offsets, output indices -- follows from ONE
+    // value, the env index e, by a mask, a shift or a multiply-add; e itself is laundered (a shuffle from the own lane:
+    // an identity the assembler cannot see through) so that nothing is rebuilt from the special registers inside the loop.
+    int e = (blockIdx.x * NW + (threadIdx.x >> 5)) * EPW + (threadIdx.x & 31) / G;
+    int lane;
+    if (G == 1) {
+        e = __shfl_sync(kFull, e, threadIdx.x & 31);
+        lane = e & 31;
+    } else {
+        lane = threadIdx.x & 31;
+        lane = __shfl_sync(kFull, lane, lane);
+        e = __shfl_sync(kFull, e, lane);
+    }
     const int grp = lane / G, gl = lane % G;
-    const int warp_env0 = (blockIdx.x * NW + warp) * EPW;
-    const int e = warp_env0 + grp;
+    const int warp = (e / EPW) & (NW - 1);                  // (blockIdx.x * NW is a multiple of NW)
+    const unsigned wb = (unsigned)(warp * WB4) * 16u;       // byte offset of this warp's block
+    const unsigned eb = wb + (unsigned)(grp * EB4) * 16u;   // ... of this env's block
     const bool valid = e < p.N;
     const bool leader = valid && gl == 0;
-    // shared memory is always addressed as array + integer offset so that it stays in the shared window
-    const int tile0 = warp * EPW * ROW4;         // this warp's tile rows
-    const int row0 = tile0 + grp * ROW4;         // this env's [older frame | newest frame]
-    const int scr0 = warp * EPW * kScr4;         // this warp's scratch rows
-    const int my0 = scr0 + grp * kScr4;
-    const int goal0 = warp * kGoals * EPW + grp;  // + g * EPW
-    const int raw0 = G > 1 ? (warp * EPW + grp) * 2 * kMaxCand : 0;
-#define row4 (s_tile + row0)
-#define myscr (s_scr + my0)
-#define stat (s_stat[warp])
+#define EBLK(i) (*reinterpret_cast<float4 *>(sm + eb + 16 * (i)))
+#define row4(i) EBLK(i)
+#define myscr(i) EBLK(SCR + (i))
+#define WROW(env, i) (*reinterpret_cast<float4 *>(sm + wb + (unsigned)(env) * (EB4 * 16) + 16 * (i)))
+    unsigned char *const srcl = reinterpret_cast<unsigned char *>(sm + wb + WX4 * 16);
+    float *const stat = reinterpret_cast<float *>(sm + wb + (WX4 + 2) * 16);
     const float L = p.lidar_len;
 
-    // lane roles in the cooperative passes
-    const int rslot = lane / kBeams;                                // ray pass: env slot 0..2 (lanes 30, 31 idle)
-    const int rj = lane - rslot * kBeams;
     if (threadIdx.x < 32) {                                         // per-lane ray direction table (body frame)
         s_ray[threadIdx.x] = p.ray_c[threadIdx.x % kBeams];
         s_ray[32 + threadIdx.x] = p.ray_s[threadIdx.x % kBeams];
     }
     if (lane < 8) stat[lane] = 0.f;
-    if (!valid && gl == 0) s_scr[my0] = make_float4(1.f, 0.f, 0.f, 0.f);      // idle groups: a defined heading for the shadow lanes
-    const int lps_sh = p.hull_max <= 8 ? 3 : (p.hull_max <= 16 ? 4 : 5);    // SAT pass: log2(lanes per env slot)
-    const int lps = 1 << lps_sh, nslots = 32 >> lps_sh;
-    const int sslot = lane >> lps_sh, sel = lane & (lps - 1);
-    const unsigned slotmask = lps == 32 ? kFull : (((1u << lps) - 1u) << (sslot * lps));
-    const int cp_row0 = lane / OBS4, cp_src0 = cp_row0 * ROW4 + lane % OBS4;      // obs copy-out: this lane's first float4
-    const int n_rows = min(EPW, p.N - warp_env0);
+    if (!valid && gl == 0) myscr(0) = make_float4(1.f, 0.f, 0.f, 0.f);      // idle groups: a defined heading for the shadow lanes
 
     EnvRegs r;
     {
@@ -89,21 +109,26 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
         closest_goal(g, r.alive, r.x, r.y, gx, gy);
         if (gl == 0) {
 #pragma unroll
-            for (int i = 0; i < kGoals; ++i) s_goal[goal0 + i * EPW] = g[i];                                              // newest frame of the resident tile = frame of the current state
-            row4[OBS4 - 4] = make_float4(r.x, r.y, (float)r.rudder, r.th);
-            row4[OBS4 - 3] = make_float4(gx, gy, l0.x, l0.y);
-            row4[OBS4 - 2] = make_float4(l0.z, l0.w, l1.x, l1.y);
-            row4[OBS4 - 1] = make_float4(l1.z, l1.w, l2.x, l2.y);
+            for (int i = 0; i < kGoals; ++i) if (!((r.alive >> i) & 1)) g[i] = make_float2(kDeadGoal, kDeadGoal);
+            EBLK(GOL) = make_float4(g[0].x, g[0].y, g[1].x, g[1].y);
+            EBLK(GOL + 1) = make_float4(g[2].x, g[2].y, g[3].x, g[3].y);
+            EBLK(GOL + 2) = make_float4(g[4].x, g[4].y, 0.f, __int_as_float(r.episode));     // .w: the episode number lives here
+            // newest frame of the resident tile = frame of the current state
+            row4(OBS4 - 4) = make_float4(r.x, r.y, (float)r.rudder, r.th);
+            row4(OBS4 - 3) = make_float4(gx, gy, l0.x, l0.y);
+            row4(OBS4 - 2) = make_float4(l0.z, l0.w, l1.x, l1.y);
+            row4(OBS4 - 1) = make_float4(l1.z, l1.w, l2.x, l2.y);
         }
     }
     float c, s, hx, hy;
     sincos_fast(r.th, s, c);
     hull_half_extents(p, c, s, hx, hy);
     uint4 cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
-    const size_t act_esize = p.action_dtype == 1 ? 8 : (p.action_dtype == 2 ? 1 : 4);
-    const size_t act_stride = (size_t)p.N * act_esize;
-    const char *ap = reinterpret_cast<const char *>(p.actions) + (size_t)(valid ? e : p.N - 1) * act_esize;
-    int a_next = load_action(p, ap, 0, p.env_id_offset + e);
+    int a_next = load_action_at(p, (size_t)min(e, p.N - 1), 0, p.env_id_offset + e);      // (idle lanes read the last env's)
+    // obs copy-out: obs rows of the warp's envs are contiguous in global memory; lane -> (row lane / OBS4, column
+    // lane % OBS4), each further round moves 32 / OBS4 rows down.  cp_lim = rows of real envs from this lane's first row
+    // on (<= 0: none): round i copies iff i * (32 / OBS4) < cp_lim.
+    const int cp_lim = (p.obs && lane < EPW * OBS4) ? min(EPW, p.N - (e - grp)) - lane / OBS4 : 0;
     __syncthreads();                             // s_ray / stat visible; also orders the tile initialisation
 
     // Iteration k >= 0 is env-step k and starts with the pose ALREADY integrated (cpBodyUpdatePosition of step k);
@@ -111,7 +136,8 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
 #pragma unroll 1
     for (int k = -1; k < p.K; ++k) {
         const bool live = k >= 0;
-        float dvx = 0.f, dvy = 0.f, dw = 0.f;
+        bool done = false, do_reset = false, goal_reached = false;
+        float reward = 0.f, gx = -1.f, gy = -1.f;
         // the candidate planes of the integrated pose: their raw records are copied global -> shared without passing
         // through registers (cp.async), in the background
         const bool near_any = leader && (cell.x | cell.y | (cell.z & 3u)) != 0u;
@@ -122,54 +148,62 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
             for (int n = 0; n < kMaxCand; ++n) {
                 const unsigned idx = (cell.w >> (8 * n)) & 0xffu;
                 if (idx != 0xffu) {
-                    cp_async16(s_raw + raw0 + 2 * n, E4 + 2 * idx);
-                    cp_async16(s_raw + raw0 + 2 * n + 1, E4 + 2 * idx + 1);
+                    cp_async16(&EBLK(RAW + 2 * n), E4 + 2 * idx);
+                    cp_async16(&EBLK(RAW + 2 * n + 1), E4 + 2 * idx + 1);
                 }
             }
         }
         if (live) {
             const int a = a_next;
-            ap += act_stride;
-            if (k + 1 < p.K) a_next = load_action(p, ap, k + 1, p.env_id_offset + e);                 // prefetch: off the critical path
             // previous frame <- newest frame of the last step / reset (SURVEY.md App. A note N2); lidar stays in place
-            if (HIST == 2 && gl == 0) { row4[0] = row4[4]; row4[1] = row4[5]; row4[2] = row4[6]; row4[3] = row4[7]; }
+            if (HIST == 2 && gl == 0) { row4(0) = row4(4); row4(1) = row4(5); row4(2) = row4(6); row4(3) = row4(7); }
 
             // ---- ShipGame.handle_discrete_action (game.py:140-153); Ship.move_forward / rotate (models.py:129-146)
-            if (a == 0) {                       // thrust along the heading the step starts from: its trig is in the row header
-                const float4 h0 = myscr[0];
-                dvx = -p.acc_dt * h0.y; dvy = p.acc_dt * h0.x; dw = -p.ang_dt * (float)r.rudder;
+            const float4 h0 = myscr(0);         // header of the pose the step starts from: its trig, and what its lidar needs
+            // The rudder angle lives in the tile, as the third value of the newest frame (exact: a small integer in fp32).
+            float dvx = 0.f, dvy = 0.f, dw = 0.f;
+            float *const rud_slot = reinterpret_cast<float *>(&row4(OBS4 - 4)) + 2;
+            const float rud = *rud_slot;
+            if (a == 0) {                       // thrust along the heading the step starts from
+                dvx = -p.acc_dt * h0.y; dvy = p.acc_dt * h0.x; dw = -p.ang_dt * rud;
             }
-            else if (a == 1) r.rudder = max(r.rudder - 5, -10);
-            else if (a == 2) r.rudder = min(r.rudder + 5, 10);
+            else if (a == 1) { if (gl == 0) *rud_slot = fmaxf(rud - 5.f, -10.f); }
+            else if (a == 2) { if (gl == 0) *rud_slot = fminf(rud + 5.f, 10.f); }
+            // ---- cpBodyUpdateVelocity: v = v*damping + f/m*dt, w = w*damping + t/I*dt.  Nothing between here and the next
+            // cpBodyUpdatePosition looks at the velocities (the overlap tests below work on the pose), so they are
+            // advanced at once instead of carrying the three force terms across the cooperative passes.
+            r.vx = r.vx * p.damping + dvx;
+            r.vy = r.vy * p.damping + dvy;
+            r.w = r.w * p.damping + dw;
 
-            // ---- LiDAR.query (models.py:39-76) at the PRE-integration pose (game.py:193 precedes :194): the scratch
+            // ---- LiDAR.query (models.py:39-76) at the PRE-integration pose (game.py:193 precedes :194): the plane
             // rows hold that pose's planes.  Up to three needy envs per pass, lanes 0-9 / 10-19 / 20-29 = their rays.
-            const int hz_own = __float_as_int(myscr[0].z);
+            const int hz_own = __float_as_int(h0.z);
             const bool big = leader && (hz_own & kHdrBig);
             const bool wants = leader && (hz_own & 0x3ff) != 0;
             const unsigned need = __ballot_sync(kFull, wants);
             if (HIST == 2) __syncwarp();        // the frame copy has read the old readings before any lane overwrites them
-            if (big) ray_query_serial(p, myscr, reinterpret_cast<float *>(s_tile + row0) + CF + 6);
+            if (big) ray_query_serial(p, &myscr(0), reinterpret_cast<float *>(&row4(0)) + CF + 6);
             if (need) {
-                // needy envs, compacted: entry q of the warp's table = the tile row of the q-th needy env
-                if (wants) s_src[warp][__popc(need & ((1u << lane) - 1u))] = (unsigned char)grp;
+                // needy envs, compacted: entry q of the warp's list = the env slot of the q-th needy env
+                if (wants) srcl[__popc(need & ((1u << lane) - 1u))] = (unsigned char)grp;
                 __syncwarp();
                 const int cnt = __popc(need);
+                const int rslot = lane / kBeams, rj = lane - rslot * kBeams;    // env slot 0..2 of the pass (lanes 30, 31 idle), ray
                 const float ray_c = s_ray[lane], ray_s = s_ray[32 + lane];
 #pragma unroll kRayPassUnroll
                 for (int q = rslot; q < cnt; q += 3) {          // lanes 30, 31 (rslot 3) only keep the others company
                     if (rslot < 3) {
-                        const int env = s_src[warp][q];
-                        const int rw = scr0 + env * kScr4;
-                        const float4 hdr = s_scr[rw];
+                        const int env = srcl[q];
+                        const float4 hdr = WROW(env, SCR);
                         const float dirx = hdr.x * ray_c - hdr.y * ray_s, diry = hdr.y * ray_c + hdr.x * ray_s;
                         const int hz = __float_as_int(hdr.z);
                         const int n = hz & 0xff;
                         float v0 = -1.f, v1 = -1.f;                     // hit distance per bank (< 0: none)
 #pragma unroll 1
                         for (int i = 0; i < n; ++i) {   // cpPolyShapeSegmentQuery: later accepted edges overwrite earlier ones
-                            const float4 e0 = s_scr[rw + 1 + 2 * i];
-                            const float2 e1 = *reinterpret_cast<const float2 *>(s_scr + rw + 2 + 2 * i);
+                            const float4 e0 = WROW(env, SCR + kRowPlane0 + 2 * i);
+                            const float2 e1 = *reinterpret_cast<const float2 *>(&WROW(env, SCR + kRowPlane0 + 1 + 2 * i));
                             float val;
                             const bool ok = ray_vs_plane(e0.x, e0.y, e0.z, e0.w, e1.x, dirx, diry, L, val);
                             if (ok && e1.y == 0.f) v0 = val;
@@ -180,93 +214,32 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                         // LiDAR.query: the first bank (list order) that reports a hit wins; misses keep the old reading
                         // (sticky vals, models.py:71)
                         const float v = v0 >= 0.f ? v0 : v1;
-                        if (v >= 0.f) reinterpret_cast<float *>(s_tile + tile0 + env * ROW4)[CF + 6 + rj] = v;
+                        if (v >= 0.f) reinterpret_cast<float *>(&WROW(env, 0))[CF + 6 + rj] = v;
                     }
                 }
             }
-            __syncwarp();                       // the rows have been read: the plane phase may overwrite them
-        }
 
-        if (G == 1 && staged) {                 // G = 1: into the scratch row, now that the ray pass is done with it
+        }
+        __syncwarp();                           // the plane rows have been read (thrust heading, ray pass): they may be rewritten
+
+        if (G == 1 && staged) {                 // G = 1: into the plane row, now that the ray pass is done with it
             const float4 *E4 = reinterpret_cast<const float4 *>(p.edges_d + (size_t)r.scen * (2 * kMaxHull));
 #pragma unroll
             for (int n = 0; n < kMaxCand; ++n) {
                 const unsigned idx = (cell.w >> (8 * n)) & 0xffu;
                 if (idx != 0xffu) {
-                    cp_async16(myscr + 1 + 2 * n, E4 + 2 * idx);
-                    cp_async16(myscr + 2 + 2 * n, E4 + 2 * idx + 1);
+                    cp_async16(&myscr(1 + 2 * n), E4 + 2 * idx);
+                    cp_async16(&myscr(2 + 2 * n), E4 + 2 * idx + 1);
                 }
             }
         }
-
-        bool done = false, do_reset = false, goal_reached = false;
-        float reward = 0.f, gx = -1.f, gy = -1.f;
-        if (live) {
-            // ---- goals (collide_goal, game.py:243-257) and the nearest remaining goal (closest_goal, game.py:333-349).
-            // The squared distance to the body origin serves both the nearest-goal search and a bounding-circle cull;
-            // only goals inside the circle are rotated into the body frame for the exact circle-vs-hull test.
-            float2 g[kGoals];
-            float gd2[kGoals];
-#pragma unroll
-            for (int i = 0; i < kGoals; ++i) {
-                g[i] = s_goal[goal0 + i * EPW];
-                const float ux = g[i].x - r.x, uy = g[i].y - r.y;
-                gd2[i] = ux * ux + uy * uy;
-            }
-            const int alive_before = r.alive;          // goal_reached <=> a goal was taken (a separate flag set inside the loops
-                                                       // below ended up in local memory at G = 1)
-            if (G == 1) {
-                // throughput-bound batches: goals inside the hull's bounding circle are tested one per loop trip (a lane
-                // rarely has more than one), then the nearest REMAINING goal is picked once for the frame
-                unsigned cand = 0u;
-#pragma unroll
-                for (int i = 0; i < kGoals; ++i)
-                    if (valid && ((r.alive >> i) & 1) && gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
-#pragma unroll 1
-                while (cand) {
-                    const int i = __ffs(cand) - 1;
-                    cand &= cand - 1u;
-                    const float2 gi = s_goal[goal0 + i * EPW];
-                    const float ux = gi.x - r.x, uy = gi.y - r.y;
-                    const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
-                    if (goal_contact(p, qx, qy)) r.alive &= ~(1 << i);
-                }
-                goal_reached = r.alive != alive_before;
-                float best = 3.0e38f;
-#pragma unroll
-                for (int i = 0; i < kGoals; ++i)
-                    if (((r.alive >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
-            } else {
-                // latency-bound batches: independent per-goal culls (no dependent chain before the branch)
-                unsigned cand = 0u;
-#pragma unroll
-                for (int i = 0; i < kGoals; ++i)
-                    if (valid && ((r.alive >> i) & 1) && gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
-                while (cand) {
-                    const int i = __ffs(cand) - 1;
-                    cand &= cand - 1u;
-                    float ux = g[0].x, uy = g[0].y;
-#pragma unroll
-                    for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
-                    ux -= r.x; uy -= r.y;
-                    const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
-                    if (goal_contact(p, qx, qy)) r.alive &= ~(1 << i);
-                }
-                goal_reached = r.alive != alive_before;
-                float best = 3.0e38f;
-#pragma unroll
-                for (int i = 0; i < kGoals; ++i)
-                    if (((r.alive >> i) & 1) && gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
-            }
-        }
-
         // ---- plane phase at the integrated pose: next step's lidar planes + this step's ship-vs-bank pre-test
         cp_async_wait_all();
         unsigned ask = 0u;
         if (leader) {
-            if (staged) ask = plane_phase<true, true>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, myscr, G > 1 ? s_raw + raw0 : myscr + 1);
-            else if (near_any) ask = plane_phase<true, false>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, myscr);
-            else myscr[0] = make_float4(c, s, 0.f, 0.f);
+            if (staged) ask = plane_phase<true, true>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, &myscr(0), G > 1 ? &EBLK(RAW) : &myscr(1));
+            else if (near_any) ask = plane_phase<true, false>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, &myscr(0));
+            else myscr(0) = make_float4(c, s, 0.f, 0.f);
         }
 
         if (live) {
@@ -276,70 +249,114 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                 // Separating-axis test for the envs the plane phase could not settle.  Contact <=> no separating axis
                 // among the edge normals of both convex polygons (touching counts: GJK distance <= 0).
                 unsigned needs = __ballot_sync(kFull, ask != 0u);
-                while (needs) {
-                    int src = -1, myslot = -1;
+                if (needs) {
+                    const int lps_sh = p.hull_max <= 8 ? 3 : (p.hull_max <= 16 ? 4 : 5);    // log2(lanes per env slot)
+                    const int lps = 1 << lps_sh, nslots = 32 >> lps_sh;
+                    const int sslot = lane >> lps_sh, sel = lane & (lps - 1);
+                    const unsigned slotmask = lps == 32 ? kFull : (((1u << lps) - 1u) << (sslot * lps));
+                    while (needs) {
+                        int src = -1, myslot = -1;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        if (q < nslots && needs) {
-                            const int t = __ffs(needs) - 1;
-                            needs &= needs - 1u;
-                            if (sslot == q) src = t;
-                            if (t / G == grp) myslot = q;
-                        }
-                    }
-                    const bool act_env = src >= 0;
-                    const int srcl = act_env ? src : lane;
-                    const float bx = __shfl_sync(kFull, r.x, srcl), by = __shfl_sync(kFull, r.y, srcl);
-                    const float bc = __shfl_sync(kFull, c, srcl), bs = __shfl_sync(kFull, s, srcl);
-                    const unsigned bsa = __shfl_sync(kFull, (unsigned)r.scen | (ask << 28), srcl);
-                    const float4 *rec = p.bank + (size_t)(bsa & 0x0fffffffu) * p.scen_stride4;
-                    const float4 hdr = __ldg(rec + 4);
-                    const float4 *bE = rec + kBankHeader4;
-                    // the edge records of both banks are requested together with the header: their addresses do not
-                    // depend on it (every slot below maxv exists), so one memory round trip serves the whole pass
-                    float4 edb[2];
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        edb[b] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (act_env && ((bsa >> (28 + b)) & 1u) && sel < p.maxv) edb[b] = __ldg(bE + b * p.maxv + sel);
-                    }
-                    float rx[kShipVerts], ry[kShipVerts];
-#pragma unroll
-                    for (int j = 0; j < kShipVerts; ++j) {
-                        rx[j] = p.ship_lx[j] * bc - p.ship_ly[j] * bs;
-                        ry[j] = p.ship_lx[j] * bs + p.ship_ly[j] * bc;
-                    }
-                    bool coll = false;
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        const bool do_b = act_env && ((bsa >> (28 + b)) & 1u) && !coll;
-                        const int nb = __float_as_int(b ? hdr.w : hdr.z);
-                        const bool actl = do_b && sel < nb;
-                        const float4 ed = edb[b];
-                        const unsigned sb = __ballot_sync(kFull, actl && bank_axis_separates(ed, rx, ry, bx, by));   // a bank edge normal separates
-                        bool sep = (sb & slotmask) != 0u;
-                        if (__ballot_sync(kFull, do_b && !sep)) {                           // else try the ship's edge normals
-#pragma unroll
-                            for (int j = 0; j < kShipVerts; ++j) {
-                                const float nx = p.ship_nx[j] * bc - p.ship_ny[j] * bs;
-                                const float ny = p.ship_nx[j] * bs + p.ship_ny[j] * bc;
-                                const float pr = actl ? nx * (ed.z - bx) + ny * (ed.w - by) : 3.0e38f;
-                                // axis j separates <=> no bank vertex of the slot reaches the hull's plane j
-                                const unsigned reach = __ballot_sync(kFull, pr <= p.ship_off[j]);
-                                sep = sep || (reach & slotmask) == 0u;
+                        for (int q = 0; q < 4; ++q) {
+                            if (q < nslots && needs) {
+                                const int t = __ffs(needs) - 1;
+                                needs &= needs - 1u;
+                                if (sslot == q) src = t;
+                                if (t / G == grp) myslot = q;
                             }
                         }
-                        if (do_b && !sep) coll = true;
+                        const bool act_env = src >= 0;
+                        const int srcl2 = act_env ? src : lane;
+                        const float bx = __shfl_sync(kFull, r.x, srcl2), by = __shfl_sync(kFull, r.y, srcl2);
+                        const float bc = __shfl_sync(kFull, c, srcl2), bs = __shfl_sync(kFull, s, srcl2);
+                        const unsigned bsa = __shfl_sync(kFull, (unsigned)r.scen | (ask << 28), srcl2);
+                        const float4 *rec = p.bank + (size_t)(bsa & 0x0fffffffu) * p.scen_stride4;
+                        const float4 hdr = __ldg(rec + 4);
+                        const float4 *bE = rec + kBankHeader4;
+                        // the edge records of both banks are requested together with the header: their addresses do not
+                        // depend on it (every slot below maxv exists), so one memory round trip serves the whole pass
+                        float4 edb[2];
+#pragma unroll
+                        for (int b = 0; b < 2; ++b) {
+                            edb[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (act_env && ((bsa >> (28 + b)) & 1u) && sel < p.maxv) edb[b] = __ldg(bE + b * p.maxv + sel);
+                        }
+                        float rx[kShipVerts], ry[kShipVerts];
+#pragma unroll
+                        for (int j = 0; j < kShipVerts; ++j) {
+                            rx[j] = p.ship_lx[j] * bc - p.ship_ly[j] * bs;
+                            ry[j] = p.ship_lx[j] * bs + p.ship_ly[j] * bc;
+                        }
+                        bool coll = false;
+#pragma unroll
+                        for (int b = 0; b < 2; ++b) {
+                            const bool do_b = act_env && ((bsa >> (28 + b)) & 1u) && !coll;
+                            const int nb = __float_as_int(b ? hdr.w : hdr.z);
+                            const bool actl = do_b && sel < nb;
+                            const float4 ed = edb[b];
+                            const unsigned sb = __ballot_sync(kFull, actl && bank_axis_separates(ed, rx, ry, bx, by));   // a bank edge normal separates
+                            bool sep = (sb & slotmask) != 0u;
+                            if (__ballot_sync(kFull, do_b && !sep)) {                           // else try the ship's edge normals
+#pragma unroll
+                                for (int j = 0; j < kShipVerts; ++j) {
+                                    const float nx = p.ship_nx[j] * bc - p.ship_ny[j] * bs;
+                                    const float ny = p.ship_nx[j] * bs + p.ship_ny[j] * bc;
+                                    const float pr = actl ? nx * (ed.z - bx) + ny * (ed.w - by) : 3.0e38f;
+                                    // axis j separates <=> no bank vertex of the slot reaches the hull's plane j
+                                    const unsigned reach = __ballot_sync(kFull, pr <= p.ship_off[j]);
+                                    sep = sep || (reach & slotmask) == 0u;
+                                }
+                            }
+                            if (do_b && !sep) coll = true;
+                        }
+                        const unsigned res = __ballot_sync(kFull, coll);
+                        if (myslot >= 0 && ((res >> (myslot * lps)) & 1u)) colliding = true;
                     }
-                    const unsigned res = __ballot_sync(kFull, coll);
-                    if (myslot >= 0 && ((res >> (myslot * lps)) & 1u)) colliding = true;
                 }
             }
 
-            // ---- cpBodyUpdateVelocity: v = v*damping + f/m*dt, w = w*damping + t/I*dt
-            r.vx = r.vx * p.damping + dvx;
-            r.vy = r.vy * p.damping + dvy;
-            r.w = r.w * p.damping + dw;
+            // ---- goals (collide_goal, game.py:243-257) and the nearest remaining goal (closest_goal, game.py:333-349).
+            // The squared distance to the body origin serves both the nearest-goal search and a bounding-circle cull;
+            // only goals inside the circle are rotated into the body frame for the exact circle-vs-hull test.  Taken
+            // goals sit at kDeadGoal: their distance is +inf, so neither the cull nor the search needs the alive mask.
+            float2 g[kGoals];
+            float gd2[kGoals];
+            {
+                const float4 ga = EBLK(GOL), gb = EBLK(GOL + 1);
+                const float2 gc = *reinterpret_cast<const float2 *>(&EBLK(GOL + 2));
+                g[0] = make_float2(ga.x, ga.y); g[1] = make_float2(ga.z, ga.w); g[2] = make_float2(gb.x, gb.y);
+                g[3] = make_float2(gb.z, gb.w); g[4] = gc;
+            }
+            unsigned cand = 0u;
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i) {
+                const float ux = g[i].x - r.x, uy = g[i].y - r.y;
+                gd2[i] = ux * ux + uy * uy;
+                if (gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
+            }
+            if (!valid) cand = 0u;
+            const int alive_before = r.alive;
+#pragma unroll 1
+            while (cand) {                      // rarely more than one trip
+                const int i = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                float ux = g[0].x, uy = g[0].y;
+#pragma unroll
+                for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
+                ux -= r.x; uy -= r.y;
+                const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
+                if (goal_contact(p, qx, qy)) {
+                    r.alive &= ~(1 << i);
+#pragma unroll
+                    for (int j = 0; j < kGoals; ++j) if (i == j) gd2[j] = __int_as_float(0x7f800000);
+                    if (gl == 0) reinterpret_cast<float2 *>(&EBLK(GOL))[i] = make_float2(kDeadGoal, kDeadGoal);
+                }
+            }
+            goal_reached = r.alive != alive_before;
+            float best = 3.0e38f;
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i)
+                if (gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
 
             // ---- ShipEnv.determine_reward (ship_env.py:62-77): collision alone does not change the value (Q12)
             const bool oob = (r.x < 0.f) || (r.x > p.W) || (r.y < 0.f) || (r.y > p.H);
@@ -352,41 +369,56 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
 
             warp_stats(stat, lane, leader, goal_reached, done, colliding, oob, timeout, all_goals, r.ret, r.steps);
             do_reset = done && p.auto_reset;
-            if (done) {
-                if (do_reset) {
-                    const int ep = r.episode + 1;
-                    reset_env(p, r, pick_scenario(p, p.env_id_offset + e, ep), ep);
-                    c = 1.f; s = 0.f;
-                    hx = 0.5f * (p.ship_aabb[2] - p.ship_aabb[0]); hy = 0.5f * (p.ship_aabb[3] - p.ship_aabb[1]);
-                    {
-                        const float4 *rec = p.bank + (size_t)r.scen * p.scen_stride4;
-                        float2 g[kGoals];
-                        const float4 rg0 = __ldg(rec + 2), rg1 = __ldg(rec + 3), rg2 = __ldg(rec + 4);
-                        unpack_goals(rg0, rg1, rg2, g);
-                        closest_goal(g, r.alive, r.x, r.y, gx, gy);
-                        if (gl == 0) {
-#pragma unroll
-                            for (int i = 0; i < kGoals; ++i) s_goal[goal0 + i * EPW] = g[i];
-                        }
-                        // the goal planes of the state change only here: written at once (a "goals changed" flag carried
-                        // to the end of the kernel had been spilled to local memory and reloaded every iteration)
-                        if (leader) store_goals(p, e, rg0, rg1, rg2);
+            if (do_reset) {
+                const int ep = __float_as_int(EBLK(GOL + 2).w) + 1;       // (only a reset needs the episode number: kept in shared memory)
+                reset_env(p, r, pick_scenario(p, p.env_id_offset + e, ep), ep);
+                c = 1.f; s = 0.f;
+                hx = 0.5f * (p.ship_aabb[2] - p.ship_aabb[0]); hy = 0.5f * (p.ship_aabb[3] - p.ship_aabb[1]);
+                {
+                    const float4 *rec = p.bank + (size_t)r.scen * p.scen_stride4;
+                    float2 gn[kGoals];
+                    const float4 rg0 = __ldg(rec + 2), rg1 = __ldg(rec + 3), rg2 = __ldg(rec + 4);
+                    unpack_goals(rg0, rg1, rg2, gn);
+                    closest_goal(gn, r.alive, r.x, r.y, gx, gy);
+                    if (gl == 0) {
+                        EBLK(GOL) = rg0; EBLK(GOL + 1) = rg1;
+                        EBLK(GOL + 2) = make_float4(rg2.x, rg2.y, 0.f, __int_as_float(ep));
                     }
-                    if (gl == 0) {              // the spawn pose's planes were evaluated when the scenario was loaded
-                        const float4 *sp = p.spawn_rows + (size_t)r.scen * kScr4;
-                        const float4 h0 = __ldg(sp);
-                        const int hn = __float_as_int(h0.z);
-                        const int nrow = (hn & kHdrBig) ? 2 : 2 * (hn & 0xff);
-                        myscr[0] = h0;
-                        for (int i = 1; i <= nrow; ++i) myscr[i] = __ldg(sp + i);
-                    }
+                    // the goal planes of the state change only here: written at once (a "goals changed" flag carried
+                    // to the end of the kernel had been spilled to local memory and reloaded every iteration)
+                    if (leader) store_goals(p, e, rg0, rg1, rg2);
+                }
+                if (gl == 0) {              // the spawn pose's planes were evaluated when the scenario was loaded
+                    const float4 *sp = p.spawn_rows + (size_t)r.scen * kScr4;
+                    const float4 h0 = __ldg(sp);
+                    const int hn = __float_as_int(h0.z);
+                    const int nrow = (hn & kHdrBig) ? 2 : 2 * (hn & 0xff);
+                    myscr(0) = h0;
+                    for (int i = 1; i <= nrow; ++i) myscr(i) = __ldg(sp + i);
                 }
             }
-
         }
-        // ---- cpSpaceStep of the NEXT step, positions first (cpBodyUpdatePosition).  Done before this step's outputs
+        if (live && gl == 0) {
+            // ---- this step's observation frame.  The leader completes the newest frame in the resident tile (the lidar
+            // slots are already there) BEFORE the pose moves on, so that no copy of this step's pose has to be kept.
+            if (do_reset) {                                     // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
+                const float4 neg = make_float4(-1.f, -1.f, -1.f, -1.f);
+                if (HIST == 2) { row4(0) = neg; row4(1) = neg; row4(2) = neg; row4(3) = neg; }
+                row4(OBS4 - 3) = make_float4(gx, gy, -1.f, -1.f);
+                row4(OBS4 - 2) = neg;
+                row4(OBS4 - 1) = neg;
+            } else {
+                reinterpret_cast<float2 *>(&row4(OBS4 - 3))[0] = make_float2(gx, gy);
+            }
+            if (do_reset) {
+                row4(OBS4 - 4) = make_float4(r.x, r.y, 0.f, r.th);      // rudder 0 (models.py:108)
+            } else {                            // the rudder slot already holds this step's angle
+                reinterpret_cast<float2 *>(&row4(OBS4 - 4))[0] = make_float2(r.x, r.y);
+                reinterpret_cast<float *>(&row4(OBS4 - 4))[3] = r.th;
+            }
+        }
+        // ---- cpSpaceStep of the NEXT step, positions first (cpBodyUpdatePosition).  Done before this step's copy-out
         // so that the grid cell of the new pose is requested as early as possible: it is consumed an iteration later.
-        const float fx = r.x, fy = r.y, fth = r.th;                 // this step's pose, for the observation frame
         if (k + 1 < p.K) {
             r.x += r.vx * p.dt;
             r.y += r.vy * p.dt;
@@ -394,34 +426,21 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
             sincos_fast(r.th, s, c);
             hull_half_extents(p, c, s, hx, hy);
             cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
+            // the next step's action, asked for here (not at the top of the step: held across the cooperative passes it
+            // was spilled, and a spilled prefetch is a synchronous load); the copy-out below covers most of its latency
+            a_next = load_action_at(p, (size_t)(k + 1) * p.N + min(e, p.N - 1), k + 1, p.env_id_offset + e);
         }
         if (live) {
-            // ---- outputs.  The leader completes the newest frame in the resident tile (lidar slots are already there);
-            // obs rows of the warp's envs are contiguous in global memory, so the tile is copied out with fully
-            // coalesced 128-bit streaming stores.
-            if (gl == 0) {
-                if (do_reset) {                                     // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
-                    const float4 neg = make_float4(-1.f, -1.f, -1.f, -1.f);
-                    if (HIST == 2) { row4[0] = neg; row4[1] = neg; row4[2] = neg; row4[3] = neg; }
-                    row4[OBS4 - 3] = make_float4(gx, gy, -1.f, -1.f);
-                    row4[OBS4 - 2] = neg;
-                    row4[OBS4 - 1] = neg;
-                } else {
-                    reinterpret_cast<float2 *>(row4 + OBS4 - 3)[0] = make_float2(gx, gy);
-                }
-                row4[OBS4 - 4] = make_float4(fx, fy, (float)r.rudder, fth);
-            }
+            // ---- outputs: obs rows of the warp's envs are contiguous in global memory, so the tile is copied out with
+            // fully coalesced 128-bit streaming stores.
             __syncwarp();
-            if (p.obs) {
-                float4 *o = p.obs + ((size_t)k * p.N + warp_env0) * OBS4 + lane;
-                if (EPW * OBS4 >= 32) {
-                    // lane -> (row lane / OBS4, column lane % OBS4); each further round moves 32 / OBS4 rows down
+            if (cp_lim > 0) {
+                const unsigned cp_src = wb + (unsigned)((lane / OBS4) * EB4 + lane % OBS4) * 16u;
+                float4 *o = p.obs + ((size_t)k * p.N + (e - grp)) * OBS4 + lane;
 #pragma unroll
-                    for (int i = 0; i < EPW * OBS4 / 32; ++i)
-                        if (cp_row0 + i * (32 / OBS4) < n_rows) __stcs(o + i * 32, s_tile[tile0 + cp_src0 + i * (32 / OBS4) * ROW4]);
-                } else if (lane < EPW * OBS4 && cp_row0 < n_rows) {
-                    __stcs(o, s_tile[tile0 + cp_src0]);
-                }
+                for (int i = 0; i < (EPW * OBS4 >= 32 ? EPW * OBS4 / 32 : 1); ++i)
+                    if (i * (32 / OBS4) < cp_lim)
+                        __stcs(o + i * 32, *reinterpret_cast<const float4 *>(sm + cp_src + i * (32 / OBS4) * (EB4 * 16)));
             }
             if (leader) {
                 const size_t row = (size_t)k * p.N + e;
@@ -429,15 +448,15 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
                 if (p.done) p.done[row] = done ? 1 : 0;
             }
         }
-        __syncwarp();                           // copy-out done and scratch rows complete before the next iteration
+        __syncwarp();                           // copy-out done and plane rows complete before the next iteration
     }
     // the loop leaves the pose of the last step in r (no integration after it)
     if (leader) {
-        const float4 l1 = row4[OBS4 - 3], l2 = row4[OBS4 - 2], l3 = row4[OBS4 - 1];
+        const float4 l1 = row4(OBS4 - 3), l2 = row4(OBS4 - 2), l3 = row4(OBS4 - 1);
+        r.episode = __float_as_int(EBLK(GOL + 2).w);
+        r.rudder = (int)row4(OBS4 - 4).z;
         store_env(p, e, r, make_float4(l1.z, l1.w, l2.x, l2.y), make_float4(l2.z, l2.w, l3.x, l3.y), l3.z, l3.w);
     }
-#undef row4
-#undef myscr
 
     // episode statistics: one red.add per non-zero value per warp into a slot row
     __syncwarp();
@@ -445,7 +464,10 @@ __global__ void __launch_bounds__(kThreads, MINB) step_kernel(const __grid_const
         const float v = stat[lane];
         if (v != 0.f) atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * kStatLen + lane, (double)v);
     }
-#undef stat
+#undef EBLK
+#undef row4
+#undef myscr
+#undef WROW
 }
 
 // plane phase at the spawn pose of every scenario (what a reset env starts from), one thread per scenario
@@ -641,20 +663,23 @@ template <int G>
 static cudaError_t launch_g(const StepParams &p, cudaStream_t stream, LaunchShape *shape)
 {
     const int envs_per_cta = kThreads / G;
-    const int blocks = (p.N + envs_per_cta - 1) / envs_per_cta;
-    if (shape) { shape->lanes_per_env = G; shape->threads = kThreads; shape->blocks = blocks; shape->window = 1; }
+    int blocks = (p.N + envs_per_cta - 1) / envs_per_cta;
+    int threads = kThreads;
     bool launched = false;
     if constexpr (G == 1) {
         if (blocks >= 148 * 8) {
-            if (p.history == 2) step_kernel<G, 2, 5><<<blocks, kThreads, 0, stream>>>(p);
-            else step_kernel<G, 1, 5><<<blocks, kThreads, 0, stream>>>(p);
+            threads = SHIPSIM_BIG_THREADS;
+            blocks = (p.N + threads - 1) / threads;
+            if (p.history == 2) step_kernel<G, 2, SHIPSIM_BIG_MIN_BLOCKS, SHIPSIM_BIG_THREADS><<<blocks, threads, 0, stream>>>(p);
+            else step_kernel<G, 1, SHIPSIM_BIG_MIN_BLOCKS, SHIPSIM_BIG_THREADS><<<blocks, threads, 0, stream>>>(p);
             launched = true;
         }
     }
     if (!launched) {
-        if (p.history == 2) step_kernel<G, 2, SHIPSIM_MIN_BLOCKS><<<blocks, kThreads, 0, stream>>>(p);
-        else step_kernel<G, 1, SHIPSIM_MIN_BLOCKS><<<blocks, kThreads, 0, stream>>>(p);
+        if (p.history == 2) step_kernel<G, 2, SHIPSIM_MIN_BLOCKS, kThreads><<<blocks, kThreads, 0, stream>>>(p);
+        else step_kernel<G, 1, SHIPSIM_MIN_BLOCKS, kThreads><<<blocks, kThreads, 0, stream>>>(p);
     }
+    if (shape) { shape->lanes_per_env = G; shape->threads = threads; shape->blocks = blocks; shape->window = 1; }
     return cudaGetLastError();
 }
 

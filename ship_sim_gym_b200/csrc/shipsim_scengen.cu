@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128) pack_bank_kernel(double *hull_xy, const i
             const double ex = v[2 * i] - v[2 * j], ey = v[2 * i + 1] - v[2 * j + 1], ln = sqrt(ex * ex + ey * ey);
             E[i] = make_float4((float)(ey / ln), (float)(-ex / ln), (float)v[2 * i], (float)v[2 * i + 1]);
             EdgeD e;
-            e.nx = ey / ln; e.ny = -ex / ln; e.vx = (float)v[2 * i]; e.vy = (float)v[2 * i + 1]; e.len = (float)ln;
+            e.set_normal(ey / ln, -ex / ln); e.vx = (float)v[2 * i]; e.vy = (float)v[2 * i + 1]; e.len = (float)ln;
             e.pad = __int_as_float(b * kMaxHull + i);
             ED[i] = e;
         }

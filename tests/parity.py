@@ -80,7 +80,8 @@ def goal_shell_states(rng, n, W, H, n_scen, deltas=(-1e-2, -5e-3, -2e-3, 2e-3, 5
     ints[:, 3] = rng.randint(0, n_scen, n)
     lidar = np.full((n, 10), -1.0)
     goals = np.zeros((n, 5, 2))
-    goals[:] = np.array([W * 5.0, H * 5.0])           # far away, except goal k
+    goals[:, :, 0] = W * 5.0 + 100.0 * np.arange(5)[None]     # far away (and at distinct distances: no nearest-goal ties), except goal k
+    goals[:, :, 1] = H * 5.0
     delta = np.asarray(deltas)[rng.randint(0, len(deltas), n)]
     c, s = np.cos(pose[:, 2]), np.sin(pose[:, 2])
     for e in range(n):
