@@ -280,18 +280,59 @@ __device__ __forceinline__ bool goal_contact(const StepParams &p, float qx, floa
 __device__ __forceinline__ void prefetch_l2(const void *ptr) { asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr)); }
 __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
-// 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, completes in the background
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+// ---------------------------------------------------------------------------------------------- shared memory by address
+// On sm_100 an access to a __shared__ array is LDS [reg + UR], where the uniform register holds the CTA's shared
+// window base, 0x400 + (CgaCtaId << 24): ptxas rebuilds it with an S2UR wherever it runs out of uniform registers, and
+// in these kernels that special-register read was the hottest stall of the loop (ncu: 14 % of the samples on one of
+// them).  The hot loops therefore address shared memory through a 32-bit shared-space address that is computed once
+// and kept in an ordinary register, with explicit ld.shared / st.shared.  (asm volatile: these keep their order among
+// themselves and relative to __syncwarp, which is all the kernels rely on.)
+__device__ __forceinline__ unsigned smem_addr(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ float4 lds4(unsigned a)
 {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
 }
+__device__ __forceinline__ float2 lds2(unsigned a)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds1(unsigned a)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned a)
+{
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts4(unsigned a, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts2(unsigned a, float2 v) { asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory"); }
+__device__ __forceinline__ void sts1(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u8(unsigned a, unsigned v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// 16-byte asynchronous global -> shared copy (LDGSTS): no register staging, completes in the background
+__device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) { cp_async16_s(smem_addr(smem_dst), gmem_src); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Episode statistics of one step for a whole warp: counters by ballot + popc, the two sums (episode return and length of
-// the envs that finished) by visiting the few finished lanes.  Lane 0 adds the totals to the warp's eight accumulators:
-// plain shared-memory read-modify-write, no atomics (measured: the shared atomics cost 4 % of the stall samples).
-__device__ __forceinline__ void warp_stats(float *stat, int lane, bool counted, bool goal_reached, bool done, bool colliding, bool oob,
+// the envs that finished) by visiting the few finished lanes.  Lane 0 adds the totals to the warp's eight accumulators
+// (shared-space address `stat`): plain shared-memory read-modify-write, no atomics (measured: the shared atomics cost 4 %
+// of the stall samples).
+__device__ __forceinline__ void warp_stats(unsigned stat, int lane, bool counted, bool goal_reached, bool done, bool colliding, bool oob,
                                            bool timeout, bool all_goals, float ep_return, int ep_steps)
 {
     const unsigned gm = __ballot_sync(kFull, counted && goal_reached);
@@ -306,8 +347,10 @@ __device__ __forceinline__ void warp_stats(float *stat, int lane, bool counted, 
         ssum += (float)__shfl_sync(kFull, ep_steps, src);
     }
     if (lane == 0) {
-        stat[0] += (float)__popc(dm); stat[1] += rsum; stat[2] += ssum; stat[3] += (float)__popc(gm);
-        stat[4] += (float)__popc(cm); stat[5] += (float)__popc(om); stat[6] += (float)__popc(tm); stat[7] += (float)__popc(am);
+        float4 a = lds4(stat), b = lds4(stat + 16);
+        a.x += (float)__popc(dm); a.y += rsum; a.z += ssum; a.w += (float)__popc(gm);
+        b.x += (float)__popc(cm); b.y += (float)__popc(om); b.z += (float)__popc(tm); b.w += (float)__popc(am);
+        sts4(stat, a); sts4(stat + 16, b);
     }
 }
 

@@ -48,12 +48,12 @@ __device__ __forceinline__ void hull_half_extents(const StepParams &p, float c, 
     float minx = 0.f, maxx = 0.f, miny = 0.f, maxy = 0.f;
 #pragma unroll
     for (int j = 1; j < kShipVerts; ++j) {
-        const float wx = p.ship_lx[j] * c - p.ship_ly[j] * s;
-        const float wy = p.ship_lx[j] * s + p.ship_ly[j] * c;
+        const float wx = fmaf(p.ship_lx[j], c, -__fmul_rn(p.ship_ly[j], s));
+        const float wy = fmaf(p.ship_lx[j], s, __fmul_rn(p.ship_ly[j], c));
         minx = fminf(minx, wx); maxx = fmaxf(maxx, wx); miny = fminf(miny, wy); maxy = fmaxf(maxy, wy);
     }
-    hx = 0.5f * (maxx - minx);
-    hy = 0.5f * (maxy - miny);
+    hx = __fmul_rn(0.5f, __fadd_rn(maxx, -minx));
+    hy = __fmul_rn(0.5f, __fadd_rn(maxy, -miny));
 }
 
 // Reach-grid cell of the lidar origin (ox, oy): which bank edges a ray starting there can touch at all.
@@ -73,10 +73,10 @@ struct PlaneEval { float d, ta, nx, ny, len; };
 
 __device__ __forceinline__ PlaneEval eval_plane_rec(const float4 nn, const float4 ev, float x, float y, float hx, float hy)
 {
-    const float qx = (x - ev.x) + hx, qy = (y - ev.y) + hy;                           // origin - v_i
+    const float qx = __fadd_rn(__fadd_rn(x, -ev.x), hx), qy = __fadd_rn(__fadd_rn(y, -ev.y), hy);     // origin - v_i
     PlaneEval o;
-    o.d = fmaf(nn.x, qx, __fmul_rn(nn.y, qy)) + fmaf(nn.z, qx, __fmul_rn(nn.w, qy));
-    o.ta = fmaf(nn.x, qy, -__fmul_rn(nn.y, qx)) + fmaf(nn.z, qy, -__fmul_rn(nn.w, qx));
+    o.d = __fadd_rn(fmaf(nn.x, qx, __fmul_rn(nn.y, qy)), fmaf(nn.z, qx, __fmul_rn(nn.w, qy)));
+    o.ta = __fadd_rn(fmaf(nn.x, qy, -__fmul_rn(nn.y, qx)), fmaf(nn.z, qy, -__fmul_rn(nn.w, qx)));
     o.nx = nn.x;
     o.ny = nn.y;
     o.len = ev.z;
@@ -101,12 +101,21 @@ __device__ __forceinline__ float rcp_approx(float x)
 // edge-extent test or the inside test has already decided).  `val` = |hit - origin|.
 __device__ __forceinline__ bool ray_vs_plane(float d, float ta, float nxl, float nyl, float len, float dirx, float diry, float L, float &val)
 {
-    const float denom = nxl * dirx + nyl * diry;                          // an - bn
-    const float cr = nxl * diry - nyl * dirx;                             // -L * cross(n, dir)
-    const float t = d * rcp_approx(denom);
-    const float tang = ta - t * cr;                                       // cross(n, hit - v_i)
-    val = t * L;
+    // (every product / sum spelled out: which operand pairs the compiler fuses would otherwise differ between the two
+    // kernels that inline this, and their results are compared bit for bit)
+    const float denom = fmaf(nxl, dirx, __fmul_rn(nyl, diry));            // an - bn
+    const float cr = fmaf(nxl, diry, -__fmul_rn(nyl, dirx));              // -L * cross(n, dir)
+    const float t = __fmul_rn(d, rcp_approx(denom));
+    const float tang = fmaf(-t, cr, ta);                                  // cross(n, hit - v_i)
+    val = __fmul_rn(t, L);
     return d >= 0.f && denom > 0.f && d <= denom && tang >= -len && tang <= 0.f;
+}
+
+// direction of ray (rc, rs) = (cos, sin of its body-frame angle) for a hull heading (c, s)
+__device__ __forceinline__ void ray_dir(float c, float s, float rc, float rs, float &dirx, float &diry)
+{
+    dirx = fmaf(c, rc, -__fmul_rn(s, rs));
+    diry = fmaf(s, rc, __fmul_rn(c, rs));
 }
 
 constexpr int kMaxCand = 4;                  // candidate planes a scratch row holds (more -> serial ray query)
@@ -126,28 +135,42 @@ __device__ __forceinline__ PlaneOut plane_at_pose(const StepParams &p, const flo
     const float L = p.lidar_len;
     const PlaneEval pe = eval_plane_rec(nn, ev, x, y, hx, hy);
     PlaneOut o;
-    o.d = pe.d; o.ta = pe.ta; o.nxl = -L * pe.nx; o.nyl = -L * pe.ny; o.len = pe.len;
+    o.d = pe.d; o.ta = pe.ta; o.nxl = __fmul_rn(-L, pe.nx); o.nyl = __fmul_rn(-L, pe.ny); o.len = pe.len;
     o.out = pe.d > 0.f;
     // the normal in the body frame, where both the hull and the ray fan are constant
-    const float bnx = pe.nx * c + pe.ny * s, bny = pe.ny * c - pe.nx * s;
+    const float bnx = fmaf(pe.nx, c, __fmul_rn(pe.ny, s)), bny = fmaf(pe.ny, c, -__fmul_rn(pe.nx, s));
     o.sep = false;
     if (WITH_SAT) {
         // does this bank plane have the whole ship in front of it?  n.(hull vertex j - v_i) = d - n.h + (R^T n).l_j
         // (vertex 0 is the body origin)
         float m = 0.f;
 #pragma unroll
-        for (int j = 1; j < kShipVerts; ++j) m = fminf(m, bnx * p.ship_lx[j] + bny * p.ship_ly[j]);
-        o.sep = pe.d - (pe.nx * hx + pe.ny * hy) + m > 0.f;
+        for (int j = 1; j < kShipVerts; ++j) m = fminf(m, fmaf(bnx, p.ship_lx[j], __fmul_rn(bny, p.ship_ly[j])));
+        o.sep = __fadd_rn(__fadd_rn(pe.d, -fmaf(pe.nx, hx, __fmul_rn(pe.ny, hy))), m) > 0.f;
     }
     // Can any ray of the fan reach this plane at all?  A ray hits only if 0 <= d <= -L n.dir (ray_vs_plane), and over
     // the fan -n.dir <= cos(max(0, angle(-n, fan axis) - half spread)).  Planes that fail (with a margin far above
     // fp32 rounding) are left out of the row: fewer planes per ray, and often no ray pass for the env at all.
-    const float cm = -(bnx * p.fan_cx + bny * p.fan_cy);
+    const float cm = -fmaf(bnx, p.fan_cx, __fmul_rn(bny, p.fan_cy));
     float reach = 1.f;
-    if (cm < p.fan_cos) reach = cm * p.fan_cos + sqrt_approx(fmaxf(1.f - cm * cm, 0.f)) * p.fan_sin;    // a bound: approx is plenty
-    o.keep = pe.d >= 0.f && pe.d <= L * reach * 1.0001f + 1.0e-3f;
+    if (cm < p.fan_cos)                                                                   // a bound: approx is plenty
+        reach = fmaf(cm, p.fan_cos, __fmul_rn(sqrt_approx(fmaxf(fmaf(-cm, cm, 1.f), 0.f)), p.fan_sin));
+    o.keep = pe.d >= 0.f && pe.d <= fmaf(__fmul_rn(L, reach), 1.0001f, 1.0e-3f);
     return o;
 }
+
+// Where a plane row lives: the hot loops keep theirs in shared memory and name it by its 32-bit shared address (see
+// "shared memory by address" in shipsim_device.cuh); the scenario-upload kernel writes rows to global memory.
+struct RowPtr {
+    float4 *p;
+    __device__ __forceinline__ void st(int i, float4 v) const { p[i] = v; }
+    __device__ __forceinline__ float4 ld(int i) const { return p[i]; }
+};
+struct RowSmem {
+    unsigned a;
+    __device__ __forceinline__ void st(int i, float4 v) const { sts4(a + 16u * (unsigned)i, v); }
+    __device__ __forceinline__ float4 ld(int i) const { return lds4(a + 16u * (unsigned)i); }
+};
 
 // Plane phase for one env at pose (x, y, c, s): fills the env's scratch row for the next lidar query and returns,
 // when WITH_SAT, bit b set <=> bank b is near and none of its candidate planes has the whole ship in front of it
@@ -166,9 +189,9 @@ __device__ __forceinline__ PlaneOut plane_at_pose(const StepParams &p, const flo
 // (Round 2 also tried this phase warp-cooperatively -- the (env, candidate) pairs of a whole warp laid out by a prefix
 // sum and evaluated one per lane: 7-12 % fewer instructions, but longer dependent chains and more live registers; it
 // measured 1 % faster at 1M envs and 4 % slower on the two latency-bound shapes.  profiles/r02_b_coop_plane_phase.md.)
-template <bool WITH_SAT, bool STAGED>
+template <bool WITH_SAT, bool STAGED, class ROW>
 __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, float y, float hx, float hy, float c, float s, int scen,
-                                                const uint4 cell, float4 *row, const float4 *raw = nullptr)
+                                                const uint4 cell, const ROW row, const ROW raw)
 {
     unsigned m0 = cell.x, m1 = cell.y;
     const unsigned near = ((m0 != 0u || (cell.z & 1u)) ? 1u : 0u) | ((m1 != 0u || (cell.z & 2u)) ? 2u : 0u);
@@ -187,8 +210,8 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
     for (int n = 0; n < ncand; ++n) {
         float4 nn, ev;
         if (STAGED) {
-            nn = raw[2 * n];
-            ev = raw[2 * n + 1];
+            nn = raw.ld(2 * n);
+            ev = raw.ld(2 * n + 1);
         } else {                                 // the next record is asked for before this one is evaluated
             nn = nn_next; ev = ev_next;
             if (n + 1 < ncand) {
@@ -205,19 +228,19 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
         if (o.sep) sepm |= bbit;
         if (o.keep) {
             if (!STAGED && nk == kMaxCand) {     // the row is full: big row (the masks are the cell's, not the walked ones)
-                row[0] = make_float4(c, s, __int_as_float(kHdrBig), 0.f);
-                row[1] = make_float4(x, y, hx, hy);
-                row[2] = make_float4(__int_as_float(scen), __uint_as_float(cell.x), __uint_as_float(cell.y), __uint_as_float(cell.z));
+                row.st(0, make_float4(c, s, __int_as_float(kHdrBig), 0.f));
+                row.st(1, make_float4(x, y, hx, hy));
+                row.st(2, make_float4(__int_as_float(scen), __uint_as_float(cell.x), __uint_as_float(cell.y), __uint_as_float(cell.z)));
                 return near & ~sepm;            // what has been proven separated stays proven
             }
-            row[kRowPlane0 + 2 * nk] = make_float4(o.d, o.ta, o.nxl, o.nyl);
-            row[kRowPlane0 + 1 + 2 * nk] = make_float4(o.len, bank1 ? 1.f : 0.f, 0.f, 0.f);
+            row.st(kRowPlane0 + 2 * nk, make_float4(o.d, o.ta, o.nxl, o.nyl));
+            row.st(kRowPlane0 + 1 + 2 * nk, make_float4(o.len, bank1 ? 1.f : 0.f, 0.f, 0.f));
             ++nk;
         }
     }
     // cpShapeSegmentQuery: start point inside the shape => alpha = 0 and `point` stays at the ray end
     const unsigned inm = cell.z & 3u & ~outm;
-    row[0] = make_float4(c, s, __int_as_float(nk | (int)(inm << 8)), 0.f);
+    row.st(0, make_float4(c, s, __int_as_float(nk | (int)(inm << 8)), 0.f));
     return near & ~sepm;
 }
 
@@ -226,7 +249,7 @@ __device__ __forceinline__ unsigned plane_phase(const StepParams &p, float x, fl
 static __device__ __noinline__ unsigned plane_phase_unstaged(const StepParams &p, float x, float y, float hx, float hy, float c, float s,
                                                              int scen, const uint4 cell, float4 *row)
 {
-    return plane_phase<true, false>(p, x, y, hx, hy, c, s, scen, cell, row);
+    return plane_phase<true, false>(p, x, y, hx, hy, c, s, scen, cell, RowPtr{row}, RowPtr{nullptr});
 }
 
 // Serial LiDAR.query of one env by one lane: only for rows that more than kMaxCand planes would have to be kept in.
@@ -249,9 +272,10 @@ static __device__ __noinline__ void ray_query_serial(const StepParams &p, const 
             out = out || (pe.d > 0.f);
 #pragma unroll
             for (int j = 0; j < kBeams; ++j) {
-                const float dirx = c * p.ray_c[j] - s * p.ray_s[j], diry = s * p.ray_c[j] + c * p.ray_s[j];
+                float dirx, diry;
+                ray_dir(c, s, p.ray_c[j], p.ray_s[j], dirx, diry);
                 float val;
-                if (ray_vs_plane(pe.d, pe.ta, -L * pe.nx, -L * pe.ny, pe.len, dirx, diry, L, val)) { v[j] = val; hitm |= 1u << j; }
+                if (ray_vs_plane(pe.d, pe.ta, __fmul_rn(-L, pe.nx), __fmul_rn(-L, pe.ny), pe.len, dirx, diry, L, val)) { v[j] = val; hitm |= 1u << j; }
             }
         }
         const bool inside = ((flags >> b) & 1u) && !out;

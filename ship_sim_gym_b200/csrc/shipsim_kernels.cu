@@ -59,11 +59,11 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     // row itself once the ray pass has finished with it
     constexpr int RAW = GOL + 3;
     constexpr int EB4 = (RAW + (G > 1 ? 2 * kMaxCand : 0)) | 1;
-    constexpr int WX4 = EPW * EB4;              // warp block: the env blocks, then 2 float4 of ray-pass list, 2 of statistics
-    constexpr int WB4 = WX4 + 4;
+    // warp block: the env blocks, then 2 float4 of ray-pass list, 2 of statistics, 5 of ray directions (cos[10], sin[10])
+    constexpr int WX4 = EPW * EB4;
+    constexpr int SRC = WX4, STA = WX4 + 2, RAY = WX4 + 4;
+    constexpr int WB4 = WX4 + 9;
     __shared__ float4 smem[NW * WB4];
-    __shared__ float s_ray[2 * 32];
-    char *const sm = reinterpret_cast<char *>(smem);
 
     // Everything a lane needs to find its data -- lane, warp, shared-memory offsets, output indices -- follows from ONE
     // value, the env index e, by a mask, a shift or a multiply-add; e itself is laundered (a shuffle from the own lane:
@@ -79,25 +79,24 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         e = __shfl_sync(kFull, e, lane);
     }
     const int grp = lane / G, gl = lane % G;
-    const int warp = (e / EPW) & (NW - 1);                  // (blockIdx.x * NW is a multiple of NW)
-    const unsigned wb = (unsigned)(warp * WB4) * 16u;       // byte offset of this warp's block
-    const unsigned eb = wb + (unsigned)(grp * EB4) * 16u;   // ... of this env's block
+    // Shared memory is addressed by 32-bit shared-space addresses held in ordinary registers (see "shared memory by
+    // address" in shipsim_device.cuh): eb = this env's block (laundered like e), wb = this warp's block, one
+    // multiply-add away.
+    unsigned eb = smem_addr(smem) + (unsigned)(((e / EPW) & (NW - 1)) * WB4 + grp * EB4) * 16u;   // (blockIdx.x * NW is a multiple of NW)
+    eb = __shfl_sync(kFull, eb, lane);
+    const unsigned wb = eb - (unsigned)(grp * EB4) * 16u;
     const bool valid = e < p.N;
     const bool leader = valid && gl == 0;
-#define EBLK(i) (*reinterpret_cast<float4 *>(sm + eb + 16 * (i)))
-#define row4(i) EBLK(i)
-#define myscr(i) EBLK(SCR + (i))
-#define WROW(env, i) (*reinterpret_cast<float4 *>(sm + wb + (unsigned)(env) * (EB4 * 16) + 16 * (i)))
-    unsigned char *const srcl = reinterpret_cast<unsigned char *>(sm + wb + WX4 * 16);
-    float *const stat = reinterpret_cast<float *>(sm + wb + (WX4 + 2) * 16);
+#define EA(i) (eb + 16u * (unsigned)(i))                     /* address of float4 i of this env's block */
+#define WA(env, i) (wb + (unsigned)(env) * (EB4 * 16u) + 16u * (unsigned)(i))
     const float L = p.lidar_len;
 
-    if (threadIdx.x < 32) {                                         // per-lane ray direction table (body frame)
-        s_ray[threadIdx.x] = p.ray_c[threadIdx.x % kBeams];
-        s_ray[32 + threadIdx.x] = p.ray_s[threadIdx.x % kBeams];
+    if (lane < kBeams) {                                            // ray direction table (body frame), one per warp
+        sts1(wb + RAY * 16 + 4 * lane, p.ray_c[lane]);
+        sts1(wb + RAY * 16 + 40 + 4 * lane, p.ray_s[lane]);
     }
-    if (lane < 8) stat[lane] = 0.f;
-    if (!valid && gl == 0) myscr(0) = make_float4(1.f, 0.f, 0.f, 0.f);      // idle groups: a defined heading for the shadow lanes
+    if (lane < 8) sts1(wb + STA * 16 + 4 * lane, 0.f);
+    if (!valid && gl == 0) sts4(EA(SCR), make_float4(1.f, 0.f, 0.f, 0.f));      // idle groups: a defined heading for the shadow lanes
 
     EnvRegs r;
     {
@@ -110,26 +109,23 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         if (gl == 0) {
 #pragma unroll
             for (int i = 0; i < kGoals; ++i) if (!((r.alive >> i) & 1)) g[i] = make_float2(kDeadGoal, kDeadGoal);
-            EBLK(GOL) = make_float4(g[0].x, g[0].y, g[1].x, g[1].y);
-            EBLK(GOL + 1) = make_float4(g[2].x, g[2].y, g[3].x, g[3].y);
-            EBLK(GOL + 2) = make_float4(g[4].x, g[4].y, 0.f, __int_as_float(r.episode));     // .w: the episode number lives here
+            sts4(EA(GOL), make_float4(g[0].x, g[0].y, g[1].x, g[1].y));
+            sts4(EA(GOL + 1), make_float4(g[2].x, g[2].y, g[3].x, g[3].y));
+            // .z, .w: the goals-alive mask and the episode number live here, not in registers (a taken goal and a reset are
+            // the only things that touch them)
+            sts4(EA(GOL + 2), make_float4(g[4].x, g[4].y, __int_as_float(r.alive), __int_as_float(r.episode)));
             // newest frame of the resident tile = frame of the current state
-            row4(OBS4 - 4) = make_float4(r.x, r.y, (float)r.rudder, r.th);
-            row4(OBS4 - 3) = make_float4(gx, gy, l0.x, l0.y);
-            row4(OBS4 - 2) = make_float4(l0.z, l0.w, l1.x, l1.y);
-            row4(OBS4 - 1) = make_float4(l1.z, l1.w, l2.x, l2.y);
+            sts4(EA(OBS4 - 4), make_float4(r.x, r.y, (float)r.rudder, r.th));
+            sts4(EA(OBS4 - 3), make_float4(gx, gy, l0.x, l0.y));
+            sts4(EA(OBS4 - 2), make_float4(l0.z, l0.w, l1.x, l1.y));
+            sts4(EA(OBS4 - 1), make_float4(l1.z, l1.w, l2.x, l2.y));
         }
     }
     float c, s, hx, hy;
     sincos_fast(r.th, s, c);
     hull_half_extents(p, c, s, hx, hy);
     uint4 cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
-    int a_next = load_action_at(p, (size_t)min(e, p.N - 1), 0, p.env_id_offset + e);      // (idle lanes read the last env's)
-    // obs copy-out: obs rows of the warp's envs are contiguous in global memory; lane -> (row lane / OBS4, column
-    // lane % OBS4), each further round moves 32 / OBS4 rows down.  cp_lim = rows of real envs from this lane's first row
-    // on (<= 0: none): round i copies iff i * (32 / OBS4) < cp_lim.
-    const int cp_lim = (p.obs && lane < EPW * OBS4) ? min(EPW, p.N - (e - grp)) - lane / OBS4 : 0;
-    __syncthreads();                             // s_ray / stat visible; also orders the tile initialisation
+    __syncwarp();                                // ray table, statistics and tile initialisation (all per warp) are in place
 
     // Iteration k >= 0 is env-step k and starts with the pose ALREADY integrated (cpBodyUpdatePosition of step k);
     // iteration -1 only runs the plane phase at the loaded pose and the first integration.
@@ -148,62 +144,54 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             for (int n = 0; n < kMaxCand; ++n) {
                 const unsigned idx = (cell.w >> (8 * n)) & 0xffu;
                 if (idx != 0xffu) {
-                    cp_async16(&EBLK(RAW + 2 * n), E4 + 2 * idx);
-                    cp_async16(&EBLK(RAW + 2 * n + 1), E4 + 2 * idx + 1);
+                    cp_async16_s(EA(RAW + 2 * n), E4 + 2 * idx);
+                    cp_async16_s(EA(RAW + 2 * n + 1), E4 + 2 * idx + 1);
                 }
             }
         }
         if (live) {
-            const int a = a_next;
+            // this step's action: asked for first, looked at after the lidar pass (kept in a register across the loop it was
+            // the one value the 96-register build spilled -- and a spilled prefetch is a synchronous load)
+            const int a = load_action_at(p, (size_t)k * p.N + min(e, p.N - 1), k, p.env_id_offset + e);   // (idle lanes read the last env's)
             // previous frame <- newest frame of the last step / reset (SURVEY.md App. A note N2); lidar stays in place
-            if (HIST == 2 && gl == 0) { row4(0) = row4(4); row4(1) = row4(5); row4(2) = row4(6); row4(3) = row4(7); }
-
-            // ---- ShipGame.handle_discrete_action (game.py:140-153); Ship.move_forward / rotate (models.py:129-146)
-            const float4 h0 = myscr(0);         // header of the pose the step starts from: its trig, and what its lidar needs
-            // The rudder angle lives in the tile, as the third value of the newest frame (exact: a small integer in fp32).
-            float dvx = 0.f, dvy = 0.f, dw = 0.f;
-            float *const rud_slot = reinterpret_cast<float *>(&row4(OBS4 - 4)) + 2;
-            const float rud = *rud_slot;
-            if (a == 0) {                       // thrust along the heading the step starts from
-                dvx = -p.acc_dt * h0.y; dvy = p.acc_dt * h0.x; dw = -p.ang_dt * rud;
+            if (HIST == 2 && gl == 0) {
+                const float4 f0 = lds4(EA(4)), f1 = lds4(EA(5)), f2 = lds4(EA(6)), f3 = lds4(EA(7));
+                sts4(EA(0), f0); sts4(EA(1), f1); sts4(EA(2), f2); sts4(EA(3), f3);
             }
-            else if (a == 1) { if (gl == 0) *rud_slot = fmaxf(rud - 5.f, -10.f); }
-            else if (a == 2) { if (gl == 0) *rud_slot = fminf(rud + 5.f, 10.f); }
-            // ---- cpBodyUpdateVelocity: v = v*damping + f/m*dt, w = w*damping + t/I*dt.  Nothing between here and the next
-            // cpBodyUpdatePosition looks at the velocities (the overlap tests below work on the pose), so they are
-            // advanced at once instead of carrying the three force terms across the cooperative passes.
-            r.vx = r.vx * p.damping + dvx;
-            r.vy = r.vy * p.damping + dvy;
-            r.w = r.w * p.damping + dw;
 
             // ---- LiDAR.query (models.py:39-76) at the PRE-integration pose (game.py:193 precedes :194): the plane
             // rows hold that pose's planes.  Up to three needy envs per pass, lanes 0-9 / 10-19 / 20-29 = their rays.
+            const float4 h0 = lds4(EA(SCR));    // header of the pose the step starts from: its trig, and what its lidar needs
             const int hz_own = __float_as_int(h0.z);
             const bool big = leader && (hz_own & kHdrBig);
             const bool wants = leader && (hz_own & 0x3ff) != 0;
             const unsigned need = __ballot_sync(kFull, wants);
             if (HIST == 2) __syncwarp();        // the frame copy has read the old readings before any lane overwrites them
-            if (big) ray_query_serial(p, &myscr(0), reinterpret_cast<float *>(&row4(0)) + CF + 6);
+            if (big) {                          // (rare: generic pointers are good enough)
+                float4 *blk = smem + ((e / EPW) & (NW - 1)) * WB4 + grp * EB4;
+                ray_query_serial(p, blk + SCR, reinterpret_cast<float *>(blk) + CF + 6);
+            }
             if (need) {
                 // needy envs, compacted: entry q of the warp's list = the env slot of the q-th needy env
-                if (wants) srcl[__popc(need & ((1u << lane) - 1u))] = (unsigned char)grp;
+                if (wants) sts_u8(wb + SRC * 16 + __popc(need & ((1u << lane) - 1u)), (unsigned)grp);
                 __syncwarp();
                 const int cnt = __popc(need);
                 const int rslot = lane / kBeams, rj = lane - rslot * kBeams;    // env slot 0..2 of the pass (lanes 30, 31 idle), ray
-                const float ray_c = s_ray[lane], ray_s = s_ray[32 + lane];
+                const float ray_c = lds1(wb + RAY * 16 + 4 * rj), ray_s = lds1(wb + RAY * 16 + 40 + 4 * rj);     // (lanes of a ray: broadcast)
 #pragma unroll kRayPassUnroll
                 for (int q = rslot; q < cnt; q += 3) {          // lanes 30, 31 (rslot 3) only keep the others company
                     if (rslot < 3) {
-                        const int env = srcl[q];
-                        const float4 hdr = WROW(env, SCR);
-                        const float dirx = hdr.x * ray_c - hdr.y * ray_s, diry = hdr.y * ray_c + hdr.x * ray_s;
+                        const unsigned ra = WA(lds_u8(wb + SRC * 16 + q), 0);      // the env's block
+                        const float4 hdr = lds4(ra + SCR * 16);
+                        float dirx, diry;
+                        ray_dir(hdr.x, hdr.y, ray_c, ray_s, dirx, diry);
                         const int hz = __float_as_int(hdr.z);
                         const int n = hz & 0xff;
                         float v0 = -1.f, v1 = -1.f;                     // hit distance per bank (< 0: none)
 #pragma unroll 1
                         for (int i = 0; i < n; ++i) {   // cpPolyShapeSegmentQuery: later accepted edges overwrite earlier ones
-                            const float4 e0 = WROW(env, SCR + kRowPlane0 + 2 * i);
-                            const float2 e1 = *reinterpret_cast<const float2 *>(&WROW(env, SCR + kRowPlane0 + 1 + 2 * i));
+                            const float4 e0 = lds4(ra + (SCR + kRowPlane0 + 2 * i) * 16);
+                            const float2 e1 = lds2(ra + (SCR + kRowPlane0 + 1 + 2 * i) * 16);
                             float val;
                             const bool ok = ray_vs_plane(e0.x, e0.y, e0.z, e0.w, e1.x, dirx, diry, L, val);
                             if (ok && e1.y == 0.f) v0 = val;
@@ -214,11 +202,27 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                         // LiDAR.query: the first bank (list order) that reports a hit wins; misses keep the old reading
                         // (sticky vals, models.py:71)
                         const float v = v0 >= 0.f ? v0 : v1;
-                        if (v >= 0.f) reinterpret_cast<float *>(&WROW(env, 0))[CF + 6 + rj] = v;
+                        if (v >= 0.f) sts1(ra + 4 * (CF + 6 + rj), v);
                     }
                 }
             }
 
+            // ---- ShipGame.handle_discrete_action (game.py:140-153); Ship.move_forward / rotate (models.py:129-146)
+            // The rudder angle lives in the tile, as the third value of the newest frame (exact: a small integer in fp32).
+            float dvx = 0.f, dvy = 0.f, dw = 0.f;
+            const unsigned rud_slot = EA(OBS4 - 4) + 8;
+            const float rud = lds1(rud_slot);
+            if (a == 0) {                       // thrust along the heading the step starts from
+                dvx = -p.acc_dt * h0.y; dvy = p.acc_dt * h0.x; dw = -p.ang_dt * rud;
+            }
+            else if (a == 1) { if (gl == 0) sts1(rud_slot, fmaxf(rud - 5.f, -10.f)); }
+            else if (a == 2) { if (gl == 0) sts1(rud_slot, fminf(rud + 5.f, 10.f)); }
+            // ---- cpBodyUpdateVelocity: v = v*damping + f/m*dt, w = w*damping + t/I*dt.  Nothing between here and the next
+            // cpBodyUpdatePosition looks at the velocities (the overlap tests below work on the pose), so they are
+            // advanced at once instead of carrying the three force terms across the cooperative passes.
+            r.vx = r.vx * p.damping + dvx;
+            r.vy = r.vy * p.damping + dvy;
+            r.w = r.w * p.damping + dw;
         }
         __syncwarp();                           // the plane rows have been read (thrust heading, ray pass): they may be rewritten
 
@@ -228,8 +232,8 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             for (int n = 0; n < kMaxCand; ++n) {
                 const unsigned idx = (cell.w >> (8 * n)) & 0xffu;
                 if (idx != 0xffu) {
-                    cp_async16(&myscr(1 + 2 * n), E4 + 2 * idx);
-                    cp_async16(&myscr(2 + 2 * n), E4 + 2 * idx + 1);
+                    cp_async16_s(EA(SCR + 1 + 2 * n), E4 + 2 * idx);
+                    cp_async16_s(EA(SCR + 2 + 2 * n), E4 + 2 * idx + 1);
                 }
             }
         }
@@ -237,9 +241,9 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         cp_async_wait_all();
         unsigned ask = 0u;
         if (leader) {
-            if (staged) ask = plane_phase<true, true>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, &myscr(0), G > 1 ? &EBLK(RAW) : &myscr(1));
-            else if (near_any) ask = plane_phase<true, false>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, &myscr(0));
-            else myscr(0) = make_float4(c, s, 0.f, 0.f);
+            if (staged) ask = plane_phase<true, true>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, RowSmem{EA(SCR)}, RowSmem{G > 1 ? EA(RAW) : EA(SCR + 1)});
+            else if (near_any) ask = plane_phase<true, false>(p, r.x, r.y, hx, hy, c, s, r.scen, cell, RowSmem{EA(SCR)}, RowSmem{0u});
+            else sts4(EA(SCR), make_float4(c, s, 0.f, 0.f));
         }
 
         if (live) {
@@ -322,8 +326,8 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             float2 g[kGoals];
             float gd2[kGoals];
             {
-                const float4 ga = EBLK(GOL), gb = EBLK(GOL + 1);
-                const float2 gc = *reinterpret_cast<const float2 *>(&EBLK(GOL + 2));
+                const float4 ga = lds4(EA(GOL)), gb = lds4(EA(GOL + 1));
+                const float2 gc = lds2(EA(GOL + 2));
                 g[0] = make_float2(ga.x, ga.y); g[1] = make_float2(ga.z, ga.w); g[2] = make_float2(gb.x, gb.y);
                 g[3] = make_float2(gb.z, gb.w); g[4] = gc;
             }
@@ -335,7 +339,6 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 if (gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
             }
             if (!valid) cand = 0u;
-            const int alive_before = r.alive;
 #pragma unroll 1
             while (cand) {                      // rarely more than one trip
                 const int i = __ffs(cand) - 1;
@@ -346,31 +349,33 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 ux -= r.x; uy -= r.y;
                 const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
                 if (goal_contact(p, qx, qy)) {
-                    r.alive &= ~(1 << i);
+                    goal_reached = true;
 #pragma unroll
                     for (int j = 0; j < kGoals; ++j) if (i == j) gd2[j] = __int_as_float(0x7f800000);
-                    if (gl == 0) reinterpret_cast<float2 *>(&EBLK(GOL))[i] = make_float2(kDeadGoal, kDeadGoal);
+                    if (gl == 0) {
+                        sts2(EA(GOL) + 8 * i, make_float2(kDeadGoal, kDeadGoal));
+                        sts1(EA(GOL + 2) + 8, __int_as_float(__float_as_int(lds1(EA(GOL + 2) + 8)) & ~(1 << i)));
+                    }
                 }
             }
-            goal_reached = r.alive != alive_before;
             float best = 3.0e38f;
 #pragma unroll
             for (int i = 0; i < kGoals; ++i)
                 if (gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
+            const bool all_goals = !(best < 3.0e38f);            // every goal taken: no finite distance left
 
             // ---- ShipEnv.determine_reward (ship_env.py:62-77): collision alone does not change the value (Q12)
             const bool oob = (r.x < 0.f) || (r.x > p.W) || (r.y < 0.f) || (r.y > p.H);
             reward = goal_reached ? 1.f : (oob ? -1.f : p.step_penalty);
             r.ret += reward;
             r.steps += 1;
-            const bool all_goals = (r.alive == 0);
             const bool timeout = (r.steps >= p.max_steps);
             done = colliding || all_goals || oob || timeout;             // ship_env.py:115-134
 
-            warp_stats(stat, lane, leader, goal_reached, done, colliding, oob, timeout, all_goals, r.ret, r.steps);
+            warp_stats(wb + STA * 16, lane, leader, goal_reached, done, colliding, oob, timeout, all_goals, r.ret, r.steps);
             do_reset = done && p.auto_reset;
             if (do_reset) {
-                const int ep = __float_as_int(EBLK(GOL + 2).w) + 1;       // (only a reset needs the episode number: kept in shared memory)
+                const int ep = __float_as_int(lds1(EA(GOL + 2) + 12)) + 1;    // (only a reset needs the episode number: kept in shared memory)
                 reset_env(p, r, pick_scenario(p, p.env_id_offset + e, ep), ep);
                 c = 1.f; s = 0.f;
                 hx = 0.5f * (p.ship_aabb[2] - p.ship_aabb[0]); hy = 0.5f * (p.ship_aabb[3] - p.ship_aabb[1]);
@@ -381,8 +386,8 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                     unpack_goals(rg0, rg1, rg2, gn);
                     closest_goal(gn, r.alive, r.x, r.y, gx, gy);
                     if (gl == 0) {
-                        EBLK(GOL) = rg0; EBLK(GOL + 1) = rg1;
-                        EBLK(GOL + 2) = make_float4(rg2.x, rg2.y, 0.f, __int_as_float(ep));
+                        sts4(EA(GOL), rg0); sts4(EA(GOL + 1), rg1);
+                        sts4(EA(GOL + 2), make_float4(rg2.x, rg2.y, __int_as_float((1 << kGoals) - 1), __int_as_float(ep)));
                     }
                     // the goal planes of the state change only here: written at once (a "goals changed" flag carried
                     // to the end of the kernel had been spilled to local memory and reloaded every iteration)
@@ -393,8 +398,8 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                     const float4 h0 = __ldg(sp);
                     const int hn = __float_as_int(h0.z);
                     const int nrow = (hn & kHdrBig) ? 2 : 2 * (hn & 0xff);
-                    myscr(0) = h0;
-                    for (int i = 1; i <= nrow; ++i) myscr(i) = __ldg(sp + i);
+                    sts4(EA(SCR), h0);
+                    for (int i = 1; i <= nrow; ++i) sts4(EA(SCR + i), __ldg(sp + i));
                 }
             }
         }
@@ -403,18 +408,15 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             // slots are already there) BEFORE the pose moves on, so that no copy of this step's pose has to be kept.
             if (do_reset) {                                     // ship_env.py:180-184: [-1 x 16 | reset frame], vals = -1
                 const float4 neg = make_float4(-1.f, -1.f, -1.f, -1.f);
-                if (HIST == 2) { row4(0) = neg; row4(1) = neg; row4(2) = neg; row4(3) = neg; }
-                row4(OBS4 - 3) = make_float4(gx, gy, -1.f, -1.f);
-                row4(OBS4 - 2) = neg;
-                row4(OBS4 - 1) = neg;
-            } else {
-                reinterpret_cast<float2 *>(&row4(OBS4 - 3))[0] = make_float2(gx, gy);
-            }
-            if (do_reset) {
-                row4(OBS4 - 4) = make_float4(r.x, r.y, 0.f, r.th);      // rudder 0 (models.py:108)
+                if (HIST == 2) { sts4(EA(0), neg); sts4(EA(1), neg); sts4(EA(2), neg); sts4(EA(3), neg); }
+                sts4(EA(OBS4 - 4), make_float4(r.x, r.y, 0.f, r.th));       // rudder 0 (models.py:108)
+                sts4(EA(OBS4 - 3), make_float4(gx, gy, -1.f, -1.f));
+                sts4(EA(OBS4 - 2), neg);
+                sts4(EA(OBS4 - 1), neg);
             } else {                            // the rudder slot already holds this step's angle
-                reinterpret_cast<float2 *>(&row4(OBS4 - 4))[0] = make_float2(r.x, r.y);
-                reinterpret_cast<float *>(&row4(OBS4 - 4))[3] = r.th;
+                sts2(EA(OBS4 - 4), make_float2(r.x, r.y));
+                sts1(EA(OBS4 - 4) + 12, r.th);
+                sts2(EA(OBS4 - 3), make_float2(gx, gy));
             }
         }
         // ---- cpSpaceStep of the NEXT step, positions first (cpBodyUpdatePosition).  Done before this step's copy-out
@@ -426,21 +428,22 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             sincos_fast(r.th, s, c);
             hull_half_extents(p, c, s, hx, hy);
             cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
-            // the next step's action, asked for here (not at the top of the step: held across the cooperative passes it
-            // was spilled, and a spilled prefetch is a synchronous load); the copy-out below covers most of its latency
-            a_next = load_action_at(p, (size_t)(k + 1) * p.N + min(e, p.N - 1), k + 1, p.env_id_offset + e);
         }
         if (live) {
             // ---- outputs: obs rows of the warp's envs are contiguous in global memory, so the tile is copied out with
             // fully coalesced 128-bit streaming stores.
             __syncwarp();
-            if (cp_lim > 0) {
-                const unsigned cp_src = wb + (unsigned)((lane / OBS4) * EB4 + lane % OBS4) * 16u;
+            // lane -> (row lane / OBS4, column lane % OBS4), each further round moves 32 / OBS4 rows down.  A round is real
+            // iff its row belongs to an env of this batch, i.e. iff its address lies before the end of this step's rows
+            // (tested against the step's end pointer, which moves with k: a loop-invariant row limit was hoisted, spilled
+            // and reloaded from local memory right here in every iteration)
+            if (p.obs && lane < EPW * OBS4) {
+                const unsigned cp_src = WA(lane / OBS4, lane % OBS4);
                 float4 *o = p.obs + ((size_t)k * p.N + (e - grp)) * OBS4 + lane;
+                const float4 *o_end = p.obs + (size_t)(k + 1) * p.N * OBS4;
 #pragma unroll
                 for (int i = 0; i < (EPW * OBS4 >= 32 ? EPW * OBS4 / 32 : 1); ++i)
-                    if (i * (32 / OBS4) < cp_lim)
-                        __stcs(o + i * 32, *reinterpret_cast<const float4 *>(sm + cp_src + i * (32 / OBS4) * (EB4 * 16)));
+                    if (o + i * 32 < o_end) __stcs(o + i * 32, lds4(cp_src + i * (32 / OBS4) * (EB4 * 16)));
             }
             if (leader) {
                 const size_t row = (size_t)k * p.N + e;
@@ -452,22 +455,21 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     }
     // the loop leaves the pose of the last step in r (no integration after it)
     if (leader) {
-        const float4 l1 = row4(OBS4 - 3), l2 = row4(OBS4 - 2), l3 = row4(OBS4 - 1);
-        r.episode = __float_as_int(EBLK(GOL + 2).w);
-        r.rudder = (int)row4(OBS4 - 4).z;
+        const float4 l1 = lds4(EA(OBS4 - 3)), l2 = lds4(EA(OBS4 - 2)), l3 = lds4(EA(OBS4 - 1));
+        r.episode = __float_as_int(lds1(EA(GOL + 2) + 12));
+        r.alive = __float_as_int(lds1(EA(GOL + 2) + 8));
+        r.rudder = (int)lds1(EA(OBS4 - 4) + 8);
         store_env(p, e, r, make_float4(l1.z, l1.w, l2.x, l2.y), make_float4(l2.z, l2.w, l3.x, l3.y), l3.z, l3.w);
     }
 
     // episode statistics: one red.add per non-zero value per warp into a slot row
     __syncwarp();
     if (lane < 8 && p.stats) {
-        const float v = stat[lane];
+        const float v = lds1(wb + STA * 16 + 4 * lane);
         if (v != 0.f) atomicAdd(p.stats + (size_t)(blockIdx.x % kStatSlots) * kStatLen + lane, (double)v);
     }
-#undef EBLK
-#undef row4
-#undef myscr
-#undef WROW
+#undef EA
+#undef WA
 }
 
 // plane phase at the spawn pose of every scenario (what a reset env starts from), one thread per scenario
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(128) build_spawn_rows_kernel(const __grid_cons
     for (int i = 0; i < kScr4; ++i) row[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float hx = 0.5f * (p.ship_aabb[2] - p.ship_aabb[0]), hy = 0.5f * (p.ship_aabb[3] - p.ship_aabb[1]);
     const uint4 cell = load_cell(p, sidx, p.spawn_x + hx, p.spawn_y + hy);
-    if ((cell.x | cell.y | (cell.z & 3u)) != 0u) plane_phase<false, false>(p, p.spawn_x, p.spawn_y, hx, hy, 1.f, 0.f, sidx, cell, row);
+    if ((cell.x | cell.y | (cell.z & 3u)) != 0u) plane_phase<false, false>(p, p.spawn_x, p.spawn_y, hx, hy, 1.f, 0.f, sidx, cell, RowPtr{row}, RowPtr{nullptr});
     else row[0] = make_float4(1.f, 0.f, 0.f, 0.f);
 }
 

@@ -78,6 +78,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
     const float L = p.lidar_len;
     const long long gid = p.env_id_offset + e;
 #define stat (s_stat[warp])
+    const unsigned stat_s = smem_addr(s_stat[warp]);
     auto ring = [](int s) { return s >= NS ? s - NS : s; };
 
     // lane roles in the cooperative passes (as in step_kernel)
@@ -120,7 +121,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
             hull_half_extents(p, c0, s0, hx, hy);
             const uint4 cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
             float4 *row = s_scr + sc0;
-            if ((cell.x | cell.y | (cell.z & 3u)) != 0u) plane_phase<false, false>(p, r.x, r.y, hx, hy, c0, s0, r.scen, cell, row);
+            if ((cell.x | cell.y | (cell.z & 3u)) != 0u) plane_phase<false, false>(p, r.x, r.y, hx, hy, c0, s0, r.scen, cell, RowPtr{row}, RowPtr{nullptr});
             else row[0] = make_float4(c0, s0, 0.f, 0.f);
         }
     }
@@ -279,7 +280,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
             cand &= cand - 1u;
             const float2 gi = s_goal[goal0 + i];
             const float ux = gi.x - mx, uy = gi.y - my;
-            const float qx = ux * mc + uy * ms, qy = -ux * ms + uy * mc;
+            const float qx = fmaf(ux, mc, __fmul_rn(uy, ms)), qy = fmaf(uy, mc, -__fmul_rn(ux, ms));
             if (goal_contact(p, qx, qy)) touch |= 1u << i;
         }
 
@@ -316,7 +317,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
         cp_async_wait_all();
         unsigned ask = 0u;
         if (staged) {
-            ask = plane_phase<true, true>(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow, myrow + 1);
+            ask = plane_phase<true, true>(p, mx, my, hx, hy, mc, ms, r.scen, cell, RowPtr{myrow}, RowPtr{myrow + 1});
         } else if (near_any) {                  // more candidates than are staged: evaluated straight from global memory
             ask = plane_phase_unstaged(p, mx, my, hx, hy, mc, ms, r.scen, cell, myrow);
         } else if (active) {
@@ -423,7 +424,8 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
                         const unsigned sw = s_src[warp][q];
                         const int rw = wsc0 + (int)(sw & 0xffffu);
                         const float4 hdr = s_scr[rw];
-                        const float dirx = hdr.x * ray_c - hdr.y * ray_s, diry = hdr.y * ray_c + hdr.x * ray_s;
+                        float dirx, diry;
+                        ray_dir(hdr.x, hdr.y, ray_c, ray_s, dirx, diry);
                         const int hz = __float_as_int(hdr.z);
                         const int n = hz & 0xff;
                         float v0 = -1.f, v1 = -1.f;
@@ -453,7 +455,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
             const float rv = __shfl_sync(kFull, reward, i, T);
             if (i <= t) my_ret += rv;
         }
-        warp_stats(stat, lane, commit, goal_reached, done, colliding, oob, timeout, all_goals, my_ret, steps_t);
+        warp_stats(stat_s, lane, commit, goal_reached, done, colliding, oob, timeout, all_goals, my_ret, steps_t);
         // this step's frame: pose, rudder, nearest remaining goal (closest_goal, game.py:333-349), and the lidar
         // readings.  Sticky readings (models.py:71): a ray that missed keeps the reading of the last step at which it
         // hit -- the latest hit at or before step t inside the window (found with a ballot per ray), else the carry's.
