@@ -294,6 +294,12 @@ __device__ __forceinline__ float4 lds4(unsigned a)
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint4 lds4u(unsigned a)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ float2 lds2(unsigned a)
 {
     float2 v;

@@ -66,6 +66,19 @@ __device__ __forceinline__ uint4 load_cell(const StepParams &p, int scen, float 
     return __ldg(p.grid + ((size_t)scen * kGridN + iy) * kGridN + ix);
 }
 
+// The same lookup as an asynchronous copy into shared memory (LDGSTS): no destination register, so the 16-byte cell does
+// not sit in four registers from the moment its pose is known until the next step looks at it, and no register
+// scoreboard is tied up by an L2 round trip (ncu: with a plain load, an unrelated instruction of the copy-out that
+// happened to share the load's scoreboard slot waited out the whole round trip: 7.7 % of the stall samples).
+__device__ __forceinline__ void fetch_cell_async(const StepParams &p, int scen, float ox, float oy, unsigned smem_dst)
+{
+    int ix = __float2int_rd((ox - p.gridp.x0) * p.gridp.inv_cx);
+    int iy = __float2int_rd((oy - p.gridp.y0) * p.gridp.inv_cy);
+    ix = min(max(ix, 0), kGridN - 1);
+    iy = min(max(iy, 0), kGridN - 1);
+    cp_async16_s(smem_dst, p.grid + ((size_t)scen * kGridN + iy) * kGridN + ix);
+}
+
 // A candidate plane seen from the ray origin (ox, oy) = (x + hx, y + hy): d = n.(o - v_i), ta = cross(n, o - v_i), with
 // the two-float normal of the record.  The difference o - v_i is formed in fp32 from fp32 inputs (exact when the two are
 // within a factor of two of each other, otherwise good to 1e-5 at map scale -- below what the fp32 pose itself carries).

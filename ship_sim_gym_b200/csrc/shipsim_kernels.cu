@@ -63,6 +63,9 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     constexpr int WX4 = EPW * EB4;
     constexpr int SRC = WX4, STA = WX4 + 2, RAY = WX4 + 4;
     constexpr int WB4 = WX4 + 9;
+    // the last float4 of an env block exists only to make the stride odd: it is the landing slot of fetch_cell_async
+    constexpr int CEL = EB4 - 1;
+    static_assert(CEL >= RAW + (G > 1 ? 2 * kMaxCand : 0), "the cell slot must not overlap the block's contents");
     __shared__ float4 smem[NW * WB4];
 
     // Everything a lane needs to find its data -- lane, warp, shared-memory offsets, output indices -- follows from ONE
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     float c, s, hx, hy;
     sincos_fast(r.th, s, c);
     hull_half_extents(p, c, s, hx, hy);
-    uint4 cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
+    fetch_cell_async(p, r.scen, r.x + hx, r.y + hy, EA(CEL));
     __syncwarp();                                // ray table, statistics and tile initialisation (all per warp) are in place
 
     // Iteration k >= 0 is env-step k and starts with the pose ALREADY integrated (cpBodyUpdatePosition of step k);
@@ -134,21 +137,6 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         const bool live = k >= 0;
         bool done = false, do_reset = false, goal_reached = false;
         float reward = 0.f, gx = -1.f, gy = -1.f;
-        // the candidate planes of the integrated pose: their raw records are copied global -> shared without passing
-        // through registers (cp.async), in the background
-        const bool near_any = leader && (cell.x | cell.y | (cell.z & 3u)) != 0u;
-        const bool staged = near_any && ((cell.z >> 8) & 0xffu) <= (unsigned)kMaxCand;
-        if (G > 1 && staged) {
-            const float4 *E4 = reinterpret_cast<const float4 *>(p.edges_d + (size_t)r.scen * (2 * kMaxHull));
-#pragma unroll
-            for (int n = 0; n < kMaxCand; ++n) {
-                const unsigned idx = (cell.w >> (8 * n)) & 0xffu;
-                if (idx != 0xffu) {
-                    cp_async16_s(EA(RAW + 2 * n), E4 + 2 * idx);
-                    cp_async16_s(EA(RAW + 2 * n + 1), E4 + 2 * idx + 1);
-                }
-            }
-        }
         if (live) {
             // this step's action: asked for first, looked at after the lidar pass (kept in a register across the loop it was
             // the one value the 96-register build spilled -- and a spilled prefetch is a synchronous load)
@@ -226,16 +214,73 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         }
         __syncwarp();                           // the plane rows have been read (thrust heading, ray pass): they may be rewritten
 
-        if (G == 1 && staged) {                 // G = 1: into the plane row, now that the ray pass is done with it
+        // the reach-grid cell of the integrated pose was asked for an iteration ago (asynchronous copy): it names the
+        // candidate planes, whose raw records are now copied global -> shared the same way -- with G = 1 into the plane
+        // row itself, which the ray pass has finished with, otherwise into the env's own staging area
+        cp_async_wait_all();
+        const uint4 cell = lds4u(EA(CEL));
+        const bool near_any = leader && (cell.x | cell.y | (cell.z & 3u)) != 0u;
+        const bool staged = near_any && ((cell.z >> 8) & 0xffu) <= (unsigned)kMaxCand;
+        if (staged) {
             const float4 *E4 = reinterpret_cast<const float4 *>(p.edges_d + (size_t)r.scen * (2 * kMaxHull));
 #pragma unroll
             for (int n = 0; n < kMaxCand; ++n) {
                 const unsigned idx = (cell.w >> (8 * n)) & 0xffu;
                 if (idx != 0xffu) {
-                    cp_async16_s(EA(SCR + 1 + 2 * n), E4 + 2 * idx);
-                    cp_async16_s(EA(SCR + 2 + 2 * n), E4 + 2 * idx + 1);
+                    cp_async16_s(EA((G > 1 ? RAW : SCR + 1) + 2 * n), E4 + 2 * idx);
+                    cp_async16_s(EA((G > 1 ? RAW : SCR + 1) + 2 * n + 1), E4 + 2 * idx + 1);
                 }
             }
+        }
+        bool all_goals = false;
+        if (live) {     // (while the candidate planes are in flight)
+            // ---- goals (collide_goal, game.py:243-257) and the nearest remaining goal (closest_goal, game.py:333-349).
+            // The squared distance to the body origin serves both the nearest-goal search and a bounding-circle cull;
+            // only goals inside the circle are rotated into the body frame for the exact circle-vs-hull test.  Taken
+            // goals sit at kDeadGoal: their distance is +inf, so neither the cull nor the search needs the alive mask.
+            float2 g[kGoals];
+            float gd2[kGoals];
+            {
+                const float4 ga = lds4(EA(GOL)), gb = lds4(EA(GOL + 1));
+                const float2 gc = lds2(EA(GOL + 2));
+                g[0] = make_float2(ga.x, ga.y); g[1] = make_float2(ga.z, ga.w); g[2] = make_float2(gb.x, gb.y);
+                g[3] = make_float2(gb.z, gb.w); g[4] = gc;
+            }
+            unsigned cand = 0u;
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i) {
+                const float ux = g[i].x - r.x, uy = g[i].y - r.y;
+                gd2[i] = ux * ux + uy * uy;
+                if (gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
+            }
+            if (!valid) cand = 0u;
+            float took = 0.f;                   // (a float: as a bool set inside the loop this flag was spilled to local memory)
+#pragma unroll 1
+            while (cand) {                      // rarely more than one trip
+                const int i = __ffs(cand) - 1;
+                cand &= cand - 1u;
+                float ux = g[0].x, uy = g[0].y;
+#pragma unroll
+                for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
+                ux -= r.x; uy -= r.y;
+                const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
+                if (goal_contact(p, qx, qy)) {
+                    took = 1.f;
+#pragma unroll
+                    for (int j = 0; j < kGoals; ++j) if (i == j) gd2[j] = __int_as_float(0x7f800000);
+                    if (gl == 0) {
+                        sts2(EA(GOL) + 8 * i, make_float2(kDeadGoal, kDeadGoal));
+                        sts1(EA(GOL + 2) + 8, __int_as_float(__float_as_int(lds1(EA(GOL + 2) + 8)) & ~(1 << i)));
+                    }
+                }
+            }
+            goal_reached = took != 0.f;
+            float best = 3.0e38f;
+#pragma unroll
+            for (int i = 0; i < kGoals; ++i)
+                if (gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
+            all_goals = !(best < 3.0e38f);            // every goal taken: no finite distance left
+
         }
         // ---- plane phase at the integrated pose: next step's lidar planes + this step's ship-vs-bank pre-test
         cp_async_wait_all();
@@ -319,51 +364,6 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 }
             }
 
-            // ---- goals (collide_goal, game.py:243-257) and the nearest remaining goal (closest_goal, game.py:333-349).
-            // The squared distance to the body origin serves both the nearest-goal search and a bounding-circle cull;
-            // only goals inside the circle are rotated into the body frame for the exact circle-vs-hull test.  Taken
-            // goals sit at kDeadGoal: their distance is +inf, so neither the cull nor the search needs the alive mask.
-            float2 g[kGoals];
-            float gd2[kGoals];
-            {
-                const float4 ga = lds4(EA(GOL)), gb = lds4(EA(GOL + 1));
-                const float2 gc = lds2(EA(GOL + 2));
-                g[0] = make_float2(ga.x, ga.y); g[1] = make_float2(ga.z, ga.w); g[2] = make_float2(gb.x, gb.y);
-                g[3] = make_float2(gb.z, gb.w); g[4] = gc;
-            }
-            unsigned cand = 0u;
-#pragma unroll
-            for (int i = 0; i < kGoals; ++i) {
-                const float ux = g[i].x - r.x, uy = g[i].y - r.y;
-                gd2[i] = ux * ux + uy * uy;
-                if (gd2[i] <= p.goal_cull_r2) cand |= 1u << i;
-            }
-            if (!valid) cand = 0u;
-#pragma unroll 1
-            while (cand) {                      // rarely more than one trip
-                const int i = __ffs(cand) - 1;
-                cand &= cand - 1u;
-                float ux = g[0].x, uy = g[0].y;
-#pragma unroll
-                for (int j = 1; j < kGoals; ++j) if (i == j) { ux = g[j].x; uy = g[j].y; }
-                ux -= r.x; uy -= r.y;
-                const float qx = ux * c + uy * s, qy = -ux * s + uy * c;
-                if (goal_contact(p, qx, qy)) {
-                    goal_reached = true;
-#pragma unroll
-                    for (int j = 0; j < kGoals; ++j) if (i == j) gd2[j] = __int_as_float(0x7f800000);
-                    if (gl == 0) {
-                        sts2(EA(GOL) + 8 * i, make_float2(kDeadGoal, kDeadGoal));
-                        sts1(EA(GOL + 2) + 8, __int_as_float(__float_as_int(lds1(EA(GOL + 2) + 8)) & ~(1 << i)));
-                    }
-                }
-            }
-            float best = 3.0e38f;
-#pragma unroll
-            for (int i = 0; i < kGoals; ++i)
-                if (gd2[i] < best) { best = gd2[i]; gx = g[i].x; gy = g[i].y; }
-            const bool all_goals = !(best < 3.0e38f);            // every goal taken: no finite distance left
-
             // ---- ShipEnv.determine_reward (ship_env.py:62-77): collision alone does not change the value (Q12)
             const bool oob = (r.x < 0.f) || (r.x > p.W) || (r.y < 0.f) || (r.y > p.H);
             reward = goal_reached ? 1.f : (oob ? -1.f : p.step_penalty);
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             r.th += r.w * p.dt;
             sincos_fast(r.th, s, c);
             hull_half_extents(p, c, s, hx, hy);
-            cell = load_cell(p, r.scen, r.x + hx, r.y + hy);
+            fetch_cell_async(p, r.scen, r.x + hx, r.y + hy, EA(CEL));
         }
         if (live) {
             // ---- outputs: obs rows of the warp's envs are contiguous in global memory, so the tile is copied out with
