@@ -183,6 +183,19 @@ int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int32_t K, floa
  * the first half is 16 x -1: the observation ShipEnv.reset returns (ship_env.py:180-184).  Pure host code, no device. */
 int shipsim_assemble_history(float *host_obs, const float *host_frames, const uint8_t *host_cut, int64_t n_rows, int64_t num_envs);
 
+/* The host half of the compacted wire format shipsim_step_host uses for HISTORY_SIZE = 2 (exposed for callers that move
+ * the data themselves, and for the CPU tests).  Per env-step a 16-byte record {bits(x), bits(y), bits(angle), word} with
+ * word = (rudder / 5 + 2) | reward code << 3 (0 = step penalty, 1 = +1, 2 = -1) | done << 5 | change mask << 8, where bit j
+ * of the mask says that slot 4 + j of the frame (gx, gy, lidar 0..9; ship_env.py:108-110) differs from the env's previous
+ * frame; the changed values follow in host_var, those of the 32 envs of block b at step k starting at
+ * host_off[k * ceil(num_envs / 32) + b], in env order then slot order.  host_cur[num_envs][16] holds the frame before
+ * the first step on entry and the frame after the last on exit.  Outputs (any may be NULL): host_obs[n_steps][num_envs]
+ * [16 * history], host_reward, host_done; with history = 2 and cut_on_done, a row whose done flag is set gets 16 x -1 as
+ * its previous frame (ship_env.py:180-184).  Pure host code, no device. */
+int shipsim_expand_delta(float *host_obs, float *host_reward, uint8_t *host_done, const uint32_t *host_rec, const uint32_t *host_off,
+                         const float *host_var, float *host_cur, int32_t n_steps, int64_t num_envs, float step_penalty,
+                         int32_t cut_on_done, int32_t history);
+
 /* Reduce the per-CTA statistic slots into dev_out[SHIPSIM_STATS_LEN] doubles (device memory, e.g. the tensor
  * handed to ncclAllReduce); clear != 0 zeroes the slots afterwards.  Replaces the counters ShipEnv keeps on the
  * Python object (ship_env.py:150,152,177). */

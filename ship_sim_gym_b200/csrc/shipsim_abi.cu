@@ -98,6 +98,14 @@ struct shipsim_handle {
     uint8_t *h_done = nullptr;               // pinned staging for the done flags when the caller does not want them
     size_t h_frames_cap = 0, h_done_cap = 0;
     float4 *d_frame0 = nullptr;
+    // compacted wire format of the host path (compact_frames_kernel / expand_delta_rows)
+    uint4 *d_rec = nullptr;                  // [K][N] records
+    unsigned *d_off = nullptr, *d_count = nullptr;   // [K][N/32] value offsets; one counter per chunk
+    uint32_t *h_rec = nullptr, *h_off = nullptr, *h_count = nullptr;     // pinned mirrors
+    float *h_var = nullptr;                  // pinned + mapped: the kernel writes the changed values straight into it
+    float *h_cur = nullptr;                  // one frame per env: the decoder's running state
+    size_t rec_cap = 0, var_cap = 0, cur_cap = 0;
+    int var_per_step = 0;                    // capacity of the value stream, floats per env-step
     HostPool *pool = nullptr;
     int64_t last_h2d = 0, last_d2h = 0;      // bytes the last shipsim_step_host moved over PCIe
     int64_t launches = 0;
@@ -312,6 +320,12 @@ extern "C" int shipsim_destroy(shipsim_t *h)
     for (auto &ev : h->copy_done) if (ev) cudaEventDestroy(ev);
     if (h->h_frames) cudaFreeHost(h->h_frames);
     if (h->h_done) cudaFreeHost(h->h_done);
+    if (h->h_rec) cudaFreeHost(h->h_rec);
+    if (h->h_off) cudaFreeHost(h->h_off);
+    if (h->h_count) cudaFreeHost(h->h_count);
+    if (h->h_var) cudaFreeHost(h->h_var);
+    if (h->h_cur) cudaFreeHost(h->h_cur);
+    cudaFree(h->d_rec); cudaFree(h->d_off); cudaFree(h->d_count);
     cudaFree(h->d_frame0);
     delete h->pool;
     cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_spawn); cudaFree(h->d_act);
@@ -581,8 +595,10 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     const size_t N = (size_t)h->cfg.num_envs;
     const size_t n = N * K;
     // With HISTORY_SIZE = 2 an observation is [frame of the previous step | frame of this step] (ship_env.py:112-113):
-    // half of every row repeats the row before it.  Only the FRAMES cross PCIe (the kernel runs in its one-frame mode);
-    // the rows are put together on the host, chunk by chunk, while later chunks are still in flight.
+    // half of every row repeats the row before it, and between consecutive frames of an env little changes besides the
+    // pose.  The kernel runs in its one-frame mode; a second kernel turns each chunk of frames into 16-byte records +
+    // a stream of changed values (~20 bytes per env-step instead of 64 + 5), only that crosses PCIe, and host threads
+    // rebuild the rows -- reset observations included -- chunk by chunk while later chunks are still in flight.
     const bool frames_only = h->cfg.history == 2 && host_obs != nullptr;
     if (K > h->stage_K) {
         cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
@@ -599,23 +615,45 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
         for (auto &ev : h->chunk_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         for (auto &ev : h->copy_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
-    uint8_t *done_dst = host_done;
+    int n_chunks = K >= 64 ? 16 : (K >= 8 ? 8 : 1);
+    if (const char *ev = std::getenv("SHIPSIM_HOST_CHUNKS")) n_chunks = std::max(1, std::min({atoi(ev), (int)shipsim_handle::kMaxChunks, (int)K}));
+    int kbeg[shipsim_handle::kMaxChunks + 1];
+    for (int c = 0; c <= n_chunks; ++c) kbeg[c] = (int)((int64_t)K * c / n_chunks);
+    const size_t nblk = (N + 31) / 32;
     if (frames_only) {
-        const size_t need = (n + N) * kFrame;                       // frame 0 = the state before the call
+        // Value stream: 8 floats per env-step of capacity (measured need on the default map: 0.9); a chunk that needs
+        // more -- it cannot happen with fewer than 8 of 12 slots changing on average -- is sent as plain frames instead.
+        h->var_per_step = 8;
+        if (n > h->rec_cap) {
+            cudaFree(h->d_rec); cudaFree(h->d_off); cudaFree(h->d_count);
+            if (h->h_rec) cudaFreeHost(h->h_rec);
+            if (h->h_off) cudaFreeHost(h->h_off);
+            if (h->h_count) cudaFreeHost(h->h_count);
+            if (h->h_var) cudaFreeHost(h->h_var);
+            h->d_rec = nullptr; h->d_off = nullptr; h->d_count = nullptr; h->h_rec = nullptr; h->h_off = nullptr; h->h_count = nullptr;
+            h->h_var = nullptr; h->rec_cap = 0;
+            CU(cudaMalloc(&h->d_rec, n * sizeof(uint4)));
+            CU(cudaMalloc(&h->d_off, (size_t)K * nblk * sizeof(unsigned)));
+            CU(cudaMalloc(&h->d_count, shipsim_handle::kMaxChunks * sizeof(unsigned)));
+            CU(cudaHostAlloc(&h->h_rec, n * sizeof(uint4), cudaHostAllocDefault));
+            CU(cudaHostAlloc(&h->h_off, (size_t)K * nblk * sizeof(unsigned), cudaHostAllocDefault));
+            CU(cudaHostAlloc(&h->h_count, shipsim_handle::kMaxChunks * sizeof(unsigned), cudaHostAllocDefault));
+            CU(cudaHostAlloc(&h->h_var, n * h->var_per_step * sizeof(float), cudaHostAllocMapped));
+            h->rec_cap = n;
+        }
+        if (N > h->cur_cap) {
+            if (h->h_cur) cudaFreeHost(h->h_cur);
+            h->h_cur = nullptr; h->cur_cap = 0;
+            CU(cudaHostAlloc(&h->h_cur, N * kFrame * sizeof(float), cudaHostAllocDefault));
+            h->cur_cap = N;
+        }
+        // fallback staging (plain frames), sized for one chunk
+        const size_t need = (size_t)(kbeg[1] - kbeg[0] + 1) * N * kFrame + N * kFrame;
         if (need > h->h_frames_cap) {
             if (h->h_frames) cudaFreeHost(h->h_frames);
             h->h_frames = nullptr; h->h_frames_cap = 0;
             CU(cudaHostAlloc(&h->h_frames, need * sizeof(float), cudaHostAllocDefault));
             h->h_frames_cap = need;
-        }
-        if (!host_done && h->cfg.auto_reset) {
-            if (n > h->h_done_cap) {
-                if (h->h_done) cudaFreeHost(h->h_done);
-                h->h_done = nullptr; h->h_done_cap = 0;
-                CU(cudaHostAlloc(&h->h_done, n, cudaHostAllocDefault));
-                h->h_done_cap = n;
-            }
-            done_dst = h->h_done;
         }
         if (!h->d_frame0) CU(cudaMalloc(&h->d_frame0, N * kFrame * sizeof(float)));
         if (!h->pool) {
@@ -625,19 +663,18 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
             h->pool = new HostPool(nt - 1);
         }
         CU(launch_frame(h->p, h->d_frame0, s));
+        CU(cudaMemsetAsync(h->d_count, 0, shipsim_handle::kMaxChunks * sizeof(unsigned), s));
         h->launches++;
     }
     CU(cudaMemcpyAsync(h->d_act, host_actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     h->last_h2d = (int64_t)(n * sizeof(int32_t));
     h->last_d2h = 0;
     // The rollout is cut into chunks of steps: while chunk i+1 is being computed on the caller's stream, the results
-    // of chunk i travel to the host on the copy stream (the D2H copy dominates: 69 B per env-step over PCIe against
-    // ~0.2 ns of kernel time) and chunk i-1 is being assembled by the host threads.
-    int n_chunks = K >= 64 ? 16 : (K >= 8 ? 8 : 1);
-    if (const char *ev = std::getenv("SHIPSIM_HOST_CHUNKS")) n_chunks = std::max(1, std::min({atoi(ev), (int)shipsim_handle::kMaxChunks, (int)K}));
-    int kbeg[shipsim_handle::kMaxChunks + 1];
-    for (int c = 0; c <= n_chunks; ++c) kbeg[c] = (int)((int64_t)K * c / n_chunks);
+    // of chunk i travel to the host on the copy stream and chunk i-1 is being expanded by the host threads.
     const size_t row_full = (size_t)kFrame * h->cfg.history;        // floats per complete row; chunk regions of d_obs are sized for it
+    float *d_var = nullptr;
+    if (frames_only) CU(cudaHostGetDevicePointer((void **)&d_var, h->h_var, 0));
+    const float4 *prev_frames = h->d_frame0;                        // the frames the next chunk's first step is compared with
     for (int c = 0; c < n_chunks; ++c) {
         const int k0 = kbeg[c], kc = kbeg[c + 1] - kbeg[c];
         if (kc <= 0) continue;
@@ -646,40 +683,72 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
         float *d_chunk = h->d_obs + off * row_full;
         const int rc2 = step_impl(h, h->d_act + off, SHIPSIM_ACTION_I32, kc, d_chunk, h->d_rew + off, h->d_done + off, stream, hist_c);
         if (rc2) return rc2;
+        if (frames_only) {
+            CU(launch_compact_frames((const float4 *)d_chunk, prev_frames, h->d_rew + off, h->d_done + off, (int)N, kc, h->cfg.step_penalty,
+                                     h->d_rec + off, h->d_off + (size_t)k0 * nblk, d_var + off * h->var_per_step,
+                                     (unsigned)std::min<size_t>((size_t)kc * N * h->var_per_step, 0xffffffffu), h->d_count + c, s));
+            h->launches++;
+            prev_frames = (const float4 *)d_chunk + ((size_t)(kc - 1) * N) * 4;
+        }
         CU(cudaEventRecord(h->chunk_done[c], s));
         CU(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
-        if (frames_only && c == 0) {
-            CU(cudaMemcpyAsync(h->h_frames, h->d_frame0, N * kFrame * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-            h->last_d2h += (int64_t)(N * kFrame * sizeof(float));
-        }
-        h->last_d2h += (int64_t)kc * N * ((host_reward ? 4 : 0) + (done_dst ? 1 : 0));
         if (frames_only) {
-            h->last_d2h += (int64_t)kc * N * kFrame * sizeof(float);
-            CU(cudaMemcpyAsync(h->h_frames + (off + N) * kFrame, d_chunk, (size_t)kc * N * kFrame * sizeof(float), cudaMemcpyDeviceToHost,
-                               h->copy_stream));
-        } else if (host_obs) {
-            h->last_d2h += (int64_t)kc * N * row_full * sizeof(float);
-            CU(cudaMemcpyAsync(host_obs + off * row_full, d_chunk, (size_t)kc * N * row_full * sizeof(float), cudaMemcpyDeviceToHost,
-                               h->copy_stream));
+            if (c == 0) {
+                CU(cudaMemcpyAsync(h->h_cur, h->d_frame0, N * kFrame * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+                h->last_d2h += (int64_t)(N * kFrame * sizeof(float));
+            }
+            CU(cudaMemcpyAsync(h->h_rec + off * 4, h->d_rec + off, (size_t)kc * N * sizeof(uint4), cudaMemcpyDeviceToHost, h->copy_stream));
+            CU(cudaMemcpyAsync(h->h_off + (size_t)k0 * nblk, h->d_off + (size_t)k0 * nblk, (size_t)kc * nblk * sizeof(unsigned),
+                               cudaMemcpyDeviceToHost, h->copy_stream));
+            CU(cudaMemcpyAsync(h->h_count + c, h->d_count + c, sizeof(unsigned), cudaMemcpyDeviceToHost, h->copy_stream));
+            h->last_d2h += (int64_t)kc * N * sizeof(uint4) + (int64_t)kc * nblk * sizeof(unsigned) + sizeof(unsigned);
+        } else {
+            h->last_d2h += (int64_t)kc * N * ((host_reward ? 4 : 0) + (host_done ? 1 : 0));
+            if (host_obs) {
+                h->last_d2h += (int64_t)kc * N * row_full * sizeof(float);
+                CU(cudaMemcpyAsync(host_obs + off * row_full, d_chunk, (size_t)kc * N * row_full * sizeof(float), cudaMemcpyDeviceToHost,
+                                   h->copy_stream));
+            }
+            if (host_reward) CU(cudaMemcpyAsync(host_reward + off, h->d_rew + off, (size_t)kc * N * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+            if (host_done) CU(cudaMemcpyAsync(host_done + off, h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, h->copy_stream));
         }
-        if (host_reward) CU(cudaMemcpyAsync(host_reward + off, h->d_rew + off, (size_t)kc * N * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-        if (done_dst) CU(cudaMemcpyAsync(done_dst + off, h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, h->copy_stream));
         CU(cudaEventRecord(h->copy_done[c], h->copy_stream));
     }
     if (frames_only) {
-        // obs[k][e] = [frame k-1 | frame k]; a step that ended an episode under auto-reset returns the reset observation
-        // [-1 x 16 | reset frame] (ship_env.py:180-184), and its frame IS the reset frame
-        const float *fr = h->h_frames;
         const bool cut = h->cfg.auto_reset != 0;
-        constexpr int kRowsPerJob = 2048;
+        const int workers = h->pool->size();
         for (int c = 0; c < n_chunks; ++c) {
-            if (kbeg[c + 1] <= kbeg[c]) continue;
+            const int k0 = kbeg[c], kc = kbeg[c + 1] - kbeg[c];
+            if (kc <= 0) continue;
             CU(cudaEventSynchronize(h->copy_done[c]));
-            const size_t r0 = (size_t)kbeg[c] * N, r1 = (size_t)kbeg[c + 1] * N;
-            const int jobs = (int)((r1 - r0 + kRowsPerJob - 1) / kRowsPerJob);
+            const size_t off = (size_t)k0 * N;
+            const size_t cap = (size_t)kc * N * h->var_per_step;
+            const unsigned count = h->h_count[c];
+            h->last_d2h += (int64_t)std::min<size_t>(count, cap) * sizeof(float);      // the value stream crossed PCIe too (zero-copy writes)
+            if (count > cap) {
+                // (never seen: more than 8 of 12 slots changing on average.)  This chunk goes home as plain frames.
+                const float *d_chunk = h->d_obs + off * row_full;
+                float *fr = h->h_frames;
+                std::memcpy(fr, h->h_cur, N * kFrame * sizeof(float));
+                CU(cudaMemcpyAsync(fr + N * kFrame, d_chunk, (size_t)kc * N * kFrame * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+                std::vector<uint8_t> dn((size_t)kc * N);
+                CU(cudaMemcpyAsync(dn.data(), h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, h->copy_stream));
+                if (host_reward) CU(cudaMemcpyAsync(host_reward + off, h->d_rew + off, (size_t)kc * N * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+                CU(cudaStreamSynchronize(h->copy_stream));
+                h->last_d2h += (int64_t)kc * N * (kFrame * sizeof(float) + 5);
+                assemble_history_rows(host_obs + off * row_full, fr, cut ? dn.data() : nullptr, 0, (size_t)kc * N, N);
+                if (host_done) std::memcpy(host_done + off, dn.data(), (size_t)kc * N);
+                std::memcpy(h->h_cur, fr + (size_t)kc * N * kFrame, N * kFrame * sizeof(float));
+                continue;
+            }
+            // env blocks are dealt out in contiguous ranges: a worker walks the chunk's steps over its own envs, whose
+            // running frames stay in its cache
+            const int jobs = (int)std::min<size_t>(nblk, (size_t)workers * 4);
             h->pool->run(jobs, [&](int j) {
-                const size_t a = r0 + (size_t)j * kRowsPerJob, b = std::min(r1, a + kRowsPerJob);
-                assemble_history_rows(host_obs, fr, cut ? done_dst : nullptr, a, b, N);
+                const size_t b0 = nblk * (size_t)j / jobs, b1 = nblk * (size_t)(j + 1) / jobs;
+                expand_delta_rows(host_obs + off * row_full, host_reward ? host_reward + off : nullptr, host_done ? host_done + off : nullptr,
+                                  h->h_rec + off * 4, h->h_off + (size_t)k0 * nblk, h->h_var + off * h->var_per_step, h->h_cur, kc, N, b0, b1,
+                                  h->cfg.step_penalty, cut, 2);
             });
         }
     }
@@ -700,6 +769,17 @@ extern "C" int shipsim_host_threads(const shipsim_t *h, int32_t *n_threads)
 {
     if (!h || !n_threads) return fail(SHIPSIM_ERR_ARG, "NULL argument");
     *n_threads = h->pool ? h->pool->size() : 0;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_expand_delta(float *host_obs, float *host_reward, uint8_t *host_done, const uint32_t *host_rec, const uint32_t *host_off,
+                                    const float *host_var, float *host_cur, int32_t n_steps, int64_t num_envs, float step_penalty,
+                                    int32_t cut_on_done, int32_t history)
+{
+    if (!host_rec || !host_off || !host_var || !host_cur || n_steps < 0 || num_envs < 1 || (history != 1 && history != 2))
+        return fail(SHIPSIM_ERR_ARG, "NULL buffer or bad sizes");
+    expand_delta_rows(host_obs, host_reward, host_done, host_rec, host_off, host_var, host_cur, n_steps, (size_t)num_envs, 0,
+                      ((size_t)num_envs + 31) / 32, step_penalty, cut_on_done != 0, history);
     return SHIPSIM_OK;
 }
 

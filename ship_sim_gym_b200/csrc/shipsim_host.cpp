@@ -5,6 +5,7 @@
 // (profiles/host_assembly_bench.cpp).
 #include "shipsim_host.h"
 
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #if defined(__x86_64__)
@@ -60,6 +61,78 @@ void assemble_history_rows(float *obs, const float *frames, const uint8_t *cut, 
     if ((((uintptr_t)obs | (uintptr_t)frames) & 15) == 0) return rows_sse2(obs, frames, cut, row_begin, row_end, N);
 #endif
     rows_plain(obs, frames, cut, row_begin, row_end, N);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Compacted wire format -> rows.  Scalar bookkeeping per row (a handful of integer operations and, on 20 % of the rows,
+// a few 4-byte patches of the env's current frame, which stays in the core's cache) around two 64-byte streaming stores.
+// ---------------------------------------------------------------------------------------------------------------------
+static inline float bits_f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
+template <int LEVEL>        // 0 plain, 1 SSE2, 2 AVX-512 (callers guarantee the alignment the level needs)
+#if defined(__x86_64__)
+__attribute__((target("avx512f")))
+#endif
+static void expand_rows_impl(float *obs, float *rew, uint8_t *done, const uint32_t *rec, const uint32_t *off, const float *var, float *cur,
+                             int kc, size_t N, size_t blk_begin, size_t blk_end, float step_penalty, bool cut_on_done, int history)
+{
+    const size_t nblk = (N + 31) / 32;
+    const float rtab[4] = {step_penalty, 1.f, -1.f, 0.f};
+    const int row_f = kF * history;
+    for (int k = 0; k < kc; ++k) {
+        for (size_t blk = blk_begin; blk < blk_end; ++blk) {
+            const float *v = var + off[(size_t)k * nblk + blk];
+            const size_t e1 = std::min(N, blk * 32 + 32);
+            for (size_t e = blk * 32; e < e1; ++e) {
+                const size_t row = (size_t)k * N + e;
+                const uint32_t *r = rec + row * 4;
+                const uint32_t word = r[3];
+                const bool dn = (word >> 5) & 1u;
+                float *c = cur + e * kF;
+                float *dst = obs ? obs + row * row_f : nullptr;
+                if (dst && history == 2) {                      // the previous frame goes out before it is overwritten
+                    const bool reset_row = cut_on_done && dn;
+#if defined(__x86_64__)
+                    if (LEVEL == 2) _mm512_stream_ps(dst, reset_row ? _mm512_set1_ps(-1.f) : _mm512_load_ps(c));
+                    else if (LEVEL == 1) for (int i = 0; i < kF; i += 4) _mm_stream_ps(dst + i, reset_row ? _mm_set1_ps(-1.f) : _mm_load_ps(c + i));
+                    else
+#endif
+                    { if (reset_row) for (int i = 0; i < kF; ++i) dst[i] = -1.f; else std::memcpy(dst, c, kF * sizeof(float)); }
+                    dst += kF;
+                }
+                c[0] = bits_f(r[0]); c[1] = bits_f(r[1]); c[3] = bits_f(r[2]);
+                c[2] = (float)(((int)(word & 7u) - 2) * 5);
+                for (uint32_t m = (word >> 8) & 0xfffu; m; m &= m - 1u) c[4 + __builtin_ctz(m)] = *v++;
+                if (dst) {
+#if defined(__x86_64__)
+                    if (LEVEL == 2) _mm512_stream_ps(dst, _mm512_load_ps(c));
+                    else if (LEVEL == 1) for (int i = 0; i < kF; i += 4) _mm_stream_ps(dst + i, _mm_load_ps(c + i));
+                    else
+#endif
+                    std::memcpy(dst, c, kF * sizeof(float));
+                }
+                if (rew) rew[row] = rtab[(word >> 3) & 3u];
+                if (done) done[row] = dn ? 1 : 0;
+            }
+        }
+    }
+#if defined(__x86_64__)
+    if (LEVEL >= 1) _mm_sfence();
+#endif
+}
+
+void expand_delta_rows(float *obs, float *rew, uint8_t *done, const uint32_t *rec, const uint32_t *off, const float *var, float *cur,
+                       int kc, size_t N, size_t blk_begin, size_t blk_end, float step_penalty, bool cut_on_done, int history)
+{
+#if defined(__x86_64__)
+    static const int level = __builtin_cpu_supports("avx512f") ? 2 : 1;
+    const uintptr_t al = (uintptr_t)obs | (uintptr_t)cur;
+    if ((al & 63) == 0 && level == 2)
+        return expand_rows_impl<2>(obs, rew, done, rec, off, var, cur, kc, N, blk_begin, blk_end, step_penalty, cut_on_done, history);
+    if ((al & 15) == 0)
+        return expand_rows_impl<1>(obs, rew, done, rec, off, var, cur, kc, N, blk_begin, blk_end, step_penalty, cut_on_done, history);
+#endif
+    expand_rows_impl<0>(obs, rew, done, rec, off, var, cur, kc, N, blk_begin, blk_end, step_penalty, cut_on_done, history);
 }
 
 }  // namespace shipsim

@@ -21,6 +21,9 @@
 // for.  Registers per thread follow from the pair: 128 x 5 -> 96, 64 x 9 -> 112, 128 x 4 / 64 x 8 -> 128.  Spills are
 // ruinous here (the L1 that would catch them is almost entirely carved out as shared memory), so the shape is chosen
 // as the most warps per SM that still compile without any.
+#ifndef SHIPSIM_SMALL_THREADS
+#define SHIPSIM_SMALL_THREADS 64
+#endif
 #ifndef SHIPSIM_BIG_THREADS
 #define SHIPSIM_BIG_THREADS 128
 #endif
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     constexpr int OBS4 = 4 * HIST;              // float4 per obs row
     // ray pass: two passes (six envs) per loop trip in the 128-register build (grids that do not fill the machine are
     // latency bound: +4 % on the hard map at 65,536 envs); the 96-register build has no room for it (-1 % at 1M envs)
-    constexpr int kRayPassUnroll = MINB * THREADS <= 512 ? 2 : 1;
+    constexpr int kRayPassUnroll = MINB * THREADS <= 512 ? 2 : 1;       // (512 threads per SM = the 128-register builds)
     constexpr int CF = 16 * (HIST - 1);         // float offset of the newest frame inside the tile row
     constexpr int NW = THREADS / 32;
     // env block: [0, OBS4) tile row = [older frame | newest frame] (lidar slots = the sticky readings);
@@ -644,6 +647,73 @@ __global__ void __launch_bounds__(256) frame_kernel(const __grid_constant__ Step
     o[3] = make_float4(l1.z, l1.w, l2.x, l2.y);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Lossless compaction of a chunk of frames for the host path (shipsim_step_host): 64 + 5 bytes per env-step shrink to
+// ~20, which is what crosses PCIe.  Between consecutive frames of an env the pose changes every step, everything else
+// rarely: rudder / reward / done are a handful of states, the nearest goal switches now and then, a lidar reading only
+// when its ray hits.  Per env-step the kernel emits one 16-byte record
+//     { x, y, angle, word }    word = rudder code | reward code << 3 | done << 5 | change mask << 8
+// (change mask: bit j set <=> slot 4 + j of the frame -- gx, gy, lidar 0..9 -- differs bitwise from the env's previous
+// frame) and appends the changed values to a variable-length stream; off[k][block] = where the values of the 32 envs
+// of a block start at step k (the blocks' order in the stream is whatever the atomics made it: the table is the truth).
+// One warp per (step, 32-env block).  The host rebuilds the frames exactly (shipsim_host.cpp: expand_delta_rows).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) compact_frames_kernel(const float4 *frames, const float4 *prev0, const float *rew, const uint8_t *done,
+                                                             int N, int kc, float step_penalty, uint4 *rec, unsigned *off, float *var,
+                                                             unsigned var_cap, unsigned *counter)
+{
+    const int lane = threadIdx.x & 31;
+    const int nblk = (N + 31) / 32;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (long long)kc * nblk) return;
+    const int k = (int)(w / nblk), blk = (int)(w % nblk);
+    const int e = blk * 32 + lane;
+    const bool valid = e < N;
+    unsigned mask = 0u;
+    float vals[12];
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (valid) {
+        const float4 *f = frames + ((size_t)k * N + e) * 4;
+        const float4 *q = k > 0 ? f - (size_t)N * 4 : prev0 + (size_t)e * 4;
+        const float4 f0 = f[0], f1 = f[1], f2 = f[2], f3 = f[3];
+        const float4 q1 = q[1], q2 = q[2], q3 = q[3];
+        const float nv[12] = {f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w, f3.x, f3.y, f3.z, f3.w};
+        const float ov[12] = {q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+            vals[j] = nv[j];
+            if (__float_as_uint(nv[j]) != __float_as_uint(ov[j])) mask |= 1u << j;
+        }
+        const float rw = rew[(size_t)k * N + e];
+        const unsigned rcode = rw == 1.f ? 1u : (rw == -1.f ? 2u : (rw == step_penalty ? 0u : 3u));     // 3 never happens
+        const unsigned rud = (unsigned)((int)f0.z / 5 + 2) & 7u;
+        r = make_uint4(__float_as_uint(f0.x), __float_as_uint(f0.y), __float_as_uint(f0.w),
+                       rud | (rcode << 3) | ((done[(size_t)k * N + e] ? 1u : 0u) << 5) | (mask << 8));
+        rec[(size_t)k * N + e] = r;
+    }
+    const int n = __popc(mask);
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(kFull, incl, 31);
+    unsigned base = 0u;
+    if (lane == 0) {
+        base = total ? atomicAdd(counter, (unsigned)total) : 0u;
+        off[(size_t)k * nblk + blk] = base;
+    }
+    base = __shfl_sync(kFull, base, 0);
+    unsigned at = base + (unsigned)(incl - n);
+#pragma unroll
+    for (int j = 0; j < 12; ++j)
+        if ((mask >> j) & 1u) {
+            if (at < var_cap) var[at] = vals[j];        // (beyond the capacity: dropped; the host sees counter > capacity)
+            ++at;
+        }
+}
+
 // stats slots -> out[kStatLen]; one warp per statistic column
 __global__ void stats_reduce_kernel(double *slots, double *out, int clear)
 {
@@ -678,8 +748,13 @@ static cudaError_t launch_g(const StepParams &p, cudaStream_t stream, LaunchShap
         }
     }
     if (!launched) {
-        if (p.history == 2) step_kernel<G, 2, SHIPSIM_MIN_BLOCKS, kThreads><<<blocks, kThreads, 0, stream>>>(p);
-        else step_kernel<G, 1, SHIPSIM_MIN_BLOCKS, kThreads><<<blocks, kThreads, 0, stream>>>(p);
+        // Grids that do not fill the machine: 64-thread CTAs (same 16 warps per SM at 128 registers), so that the few
+        // CTAs spread evenly -- 65,536 envs are 512 CTAs of 128 threads, 3.46 per SM: every SM waits for the ones that got 4
+        constexpr int T = SHIPSIM_SMALL_THREADS, MB = SHIPSIM_MIN_BLOCKS * kThreads / SHIPSIM_SMALL_THREADS;
+        threads = T;
+        blocks = (p.N + T / G - 1) / (T / G);
+        if (p.history == 2) step_kernel<G, 2, MB, T><<<blocks, T, 0, stream>>>(p);
+        else step_kernel<G, 1, MB, T><<<blocks, T, 0, stream>>>(p);
     }
     if (shape) { shape->lanes_per_env = G; shape->threads = threads; shape->blocks = blocks; shape->window = 1; }
     return cudaGetLastError();
@@ -709,6 +784,16 @@ cudaError_t launch_reset(const StepParams &p, const uint8_t *mask, const int *sc
 cudaError_t launch_clamp_scenarios(float4 *state, int N, int n_scen, cudaStream_t stream)
 {
     clamp_scenarios_kernel<<<(N + 255) / 256, 256, 0, stream>>>(state, N, n_scen);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compact_frames(const float4 *frames, const float4 *prev0, const float *rew, const uint8_t *done, int N, int kc,
+                                  float step_penalty, uint4 *rec, unsigned *off, float *var, unsigned var_cap, unsigned *counter,
+                                  cudaStream_t stream)
+{
+    const long long warps = (long long)kc * ((N + 31) / 32);
+    compact_frames_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(frames, prev0, rew, done, N, kc, step_penalty, rec, off,
+                                                                                   var, var_cap, counter);
     return cudaGetLastError();
 }
 

@@ -149,6 +149,85 @@ def test_history_rows_from_frames_host_code(align):
         _abi.check(L.shipsim_assemble_history(None, fr.ctypes.data, None, 1, N))
 
 
+def _encode_delta(frames, rew, done, step_penalty, rng):
+    """numpy statement of compact_frames_kernel's wire format (include/shipsim.h: shipsim_expand_delta); the value
+    blocks are laid out in a shuffled order, as the device's atomics may."""
+    K, N = rew.shape
+    nblk = (N + 31) // 32
+    bits = frames.view(np.uint32)
+    rec = np.zeros((K, N, 4), dtype=np.uint32)
+    off = np.zeros((K, nblk), dtype=np.uint32)
+    chunks, pos = [], 0
+    order = [(k, b) for k in range(K) for b in range(nblk)]
+    rng.shuffle(order)
+    for k, b in order:
+        off[k, b] = pos
+        for e in range(b * 32, min(N, b * 32 + 32)):
+            ch = bits[k + 1, e, 4:] != bits[k, e, 4:]
+            mask = int(sum(1 << j for j in range(12) if ch[j]))
+            r = rew[k, e]
+            rcode = 1 if r == 1.0 else (2 if r == -1.0 else 0)
+            rud = int(frames[k + 1, e, 2]) // 5 + 2
+            rec[k, e] = (bits[k + 1, e, 0], bits[k + 1, e, 1], bits[k + 1, e, 3], rud | rcode << 3 | int(done[k, e]) << 5 | mask << 8)
+            chunks.append(frames[k + 1, e, 4:][ch])
+            pos += int(ch.sum())
+    var = np.concatenate(chunks + [np.zeros(1, np.float32)]).astype(np.float32)
+    return rec, off, var
+
+
+@pytest.mark.parametrize("align,history,cut", [(0, 2, 1), (16, 2, 1), (4, 2, 0), (0, 1, 1)])
+def test_compacted_frames_expand_to_the_same_rows(align, history, cut):
+    """shipsim_expand_delta (host half of the compacted wire format of shipsim_step_host): 16-byte records + changed
+    values expand to exactly the rows shipsim_assemble_history builds from plain frames -- reset rows, rewards and done
+    flags included -- for ragged env counts (last block partly filled) and all three store paths.  No device."""
+    from ship_sim_gym_b200 import _abi
+    L = _abi.load()
+    rng = np.random.RandomState(1)
+    N, K, pen = 75, 41, np.float32(-0.01)
+    frames = np.empty((K + 1, N, 16), dtype=np.float32)
+    frames[0] = rng.randn(N, 16)
+    frames[0, :, 2] = rng.choice([-10, -5, 0, 5, 10], N)
+    for k in range(K):                                   # pose changes every step, the other slots now and then
+        frames[k + 1] = frames[k]
+        frames[k + 1, :, [0, 1, 3]] = rng.randn(3, N)
+        frames[k + 1, :, 2] = rng.choice([-10, -5, 0, 5, 10], N)
+        ch = rng.rand(N, 12) < 0.15
+        frames[k + 1, :, 4:][ch] = rng.randn(int(ch.sum()))
+    frames[3, 5, 4] = -0.0                               # bitwise change, equal as floats
+    frames[2, 5, 4] = 0.0
+    done = (rng.rand(K, N) < 0.1).astype(np.uint8)
+    rew = np.where(done != 0, rng.choice([1.0, -1.0, float(pen)], (K, N)), rng.choice([1.0, float(pen)], (K, N), p=[0.1, 0.9])).astype(np.float32)
+    rec, off, var = _encode_delta(frames, rew, done, pen, rng)
+    want = np.empty((K, N, 16 * history), dtype=np.float32)
+    want[:, :, -16:] = frames[1:]
+    if history == 2:
+        want[:, :, :16] = frames[:-1]
+        if cut:
+            want[done != 0, :16] = -1.0
+
+    def aligned(n_floats, knock=0):
+        raw = np.zeros(n_floats + 32, dtype=np.float32)
+        o = ((-raw.ctypes.data) % 64) // 4 + knock // 4
+        return raw[o:o + n_floats]
+    out = aligned(want.size, align)
+    cur = aligned(N * 16)
+    cur[:] = frames[0].ravel()
+    r_out, d_out = np.zeros((K, N), np.float32), np.zeros((K, N), np.uint8)
+    _abi.check(L.shipsim_expand_delta(out.ctypes.data, r_out.ctypes.data, d_out.ctypes.data, rec.ctypes.data, off.ctypes.data, var.ctypes.data,
+                                      cur.ctypes.data, K, N, float(pen), cut, history))
+    assert np.array_equal(out.view(np.uint32).reshape(want.shape), want.view(np.uint32))
+    assert np.array_equal(r_out, rew) and np.array_equal(d_out, done)
+    assert np.array_equal(cur.view(np.uint32).reshape(N, 16), frames[K].view(np.uint32))      # running frames = the last step's
+    # outputs are optional; the running frames still advance
+    cur[:] = frames[0].ravel()
+    _abi.check(L.shipsim_expand_delta(None, None, None, rec.ctypes.data, off.ctypes.data, var.ctypes.data, cur.ctypes.data, K, N, float(pen), cut, history))
+    assert np.array_equal(cur.view(np.uint32).reshape(N, 16), frames[K].view(np.uint32))
+    with pytest.raises(ValueError):
+        _abi.check(L.shipsim_expand_delta(out.ctypes.data, None, None, None, off.ctypes.data, var.ctypes.data, cur.ctypes.data, K, N, float(pen), cut, history))
+    with pytest.raises(ValueError):
+        _abi.check(L.shipsim_expand_delta(out.ctypes.data, None, None, rec.ctypes.data, off.ctypes.data, var.ctypes.data, cur.ctypes.data, K, N, float(pen), cut, 3))
+
+
 def test_rollout_collector_fused_policy_and_gae_on_cpu():
     """RolloutCollector runs the two trunks of MlpPolicy as one block-diagonal network (observation scale folded into
     layer 1) and computes GAE from deltas of all steps at once: both agree with the plain formulation (train/
