@@ -14,6 +14,7 @@
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -34,13 +35,18 @@ public:
         cv_.notify_all();
         for (auto &t : workers_) t.join();
     }
-    void run(int n, const std::function<void(int)> &fn)
+    void run(int n, const std::function<void(int)> &fn) { start(n, fn); finish(); }
+    // start(): the workers begin on fn(0..n-1) and the caller carries on; finish(): the caller joins in and waits for all
+    void start(int n, const std::function<void(int)> &fn)
     {
         {
             std::lock_guard<std::mutex> lk(m_);
             fn_ = &fn; n_ = n; next_.store(0); pending_ = (int)workers_.size(); ++gen_;
         }
         cv_.notify_all();
+    }
+    void finish()
+    {
         drain();
         std::unique_lock<std::mutex> lk(m_);
         done_cv_.wait(lk, [this] { return pending_ == 0; });
@@ -93,19 +99,26 @@ struct shipsim_handle {
     int stage_K = 0;
     cudaStream_t copy_stream = nullptr;      // shipsim_step_host: results of chunk i go home while chunk i+1 is computed
     static constexpr int kMaxChunks = 64;
-    cudaEvent_t chunk_done[kMaxChunks] = {}, copy_done[kMaxChunks] = {};
-    float *h_frames = nullptr;               // pinned staging: frame of the state before the call + one frame per env-step
-    uint8_t *h_done = nullptr;               // pinned staging for the done flags when the caller does not want them
-    size_t h_frames_cap = 0, h_done_cap = 0;
+    cudaEvent_t chunk_done[kMaxChunks] = {}, copy_done[kMaxChunks] = {}, trace0 = nullptr, trace_mid[kMaxChunks] = {};
     float4 *d_frame0 = nullptr;
     // compacted wire format of the host path (compact_frames_kernel / expand_delta_rows)
     uint4 *d_rec = nullptr;                  // [K][N] records
     unsigned *d_off = nullptr, *d_count = nullptr;   // [K][N/32] value offsets; one counter per chunk
     uint32_t *h_rec = nullptr, *h_off = nullptr, *h_count = nullptr;     // pinned mirrors
-    float *h_var = nullptr;                  // pinned + mapped: the kernel writes the changed values straight into it
+    float *h_var = nullptr, *d_var = nullptr;   // the changed values (a dense stream per chunk), host mirror and device buffer
+    double var_density = 2.0;                // floats per env-step the speculative D2H copy of a chunk's values is sized for
+    cudaStream_t aux_stream = nullptr;       // actions of chunks 1.. go up here; the (rare) rest of a chunk's values comes down
+    cudaEvent_t act_up = nullptr;
     float *h_cur = nullptr;                  // one frame per env: the decoder's running state
     size_t rec_cap = 0, var_cap = 0, cur_cap = 0;
     int var_per_step = 0;                    // capacity of the value stream, floats per env-step
+    // the envs [0, dma_envs) go home as complete rows by DMA, the others compacted + expanded by the host threads
+    float *d_rows = nullptr;                 // [K][dma_envs][32]
+    size_t rows_cap = 0;
+    int dma_envs = -1;                       // -1: not chosen yet
+    int dma_for_n = 0, dma_for_k = 0;
+    int dma_step = 0, dma_dir = 1;           // the split climbs towards the shorter call: step size and direction
+    double dma_last_t = 0.0;                 // seconds per env-step of the previous call
     HostPool *pool = nullptr;
     int64_t last_h2d = 0, last_d2h = 0;      // bytes the last shipsim_step_host moved over PCIe
     int64_t launches = 0;
@@ -318,14 +331,15 @@ extern "C" int shipsim_destroy(shipsim_t *h)
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     for (auto &ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->copy_done) if (ev) cudaEventDestroy(ev);
-    if (h->h_frames) cudaFreeHost(h->h_frames);
-    if (h->h_done) cudaFreeHost(h->h_done);
+    if (h->trace0) cudaEventDestroy(h->trace0);
     if (h->h_rec) cudaFreeHost(h->h_rec);
     if (h->h_off) cudaFreeHost(h->h_off);
     if (h->h_count) cudaFreeHost(h->h_count);
     if (h->h_var) cudaFreeHost(h->h_var);
     if (h->h_cur) cudaFreeHost(h->h_cur);
-    cudaFree(h->d_rec); cudaFree(h->d_off); cudaFree(h->d_count);
+    cudaFree(h->d_rec); cudaFree(h->d_off); cudaFree(h->d_count); cudaFree(h->d_rows); cudaFree(h->d_var);
+    if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
+    if (h->act_up) cudaEventDestroy(h->act_up);
     cudaFree(h->d_frame0);
     delete h->pool;
     cudaFree(h->d_bank); cudaFree(h->d_edges); cudaFree(h->d_grid); cudaFree(h->d_spawn); cudaFree(h->d_act);
@@ -596,10 +610,16 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     const size_t n = N * K;
     // With HISTORY_SIZE = 2 an observation is [frame of the previous step | frame of this step] (ship_env.py:112-113):
     // half of every row repeats the row before it, and between consecutive frames of an env little changes besides the
-    // pose.  The kernel runs in its one-frame mode; a second kernel turns each chunk of frames into 16-byte records +
-    // a stream of changed values (~20 bytes per env-step instead of 64 + 5), only that crosses PCIe, and host threads
-    // rebuild the rows -- reset observations included -- chunk by chunk while later chunks are still in flight.
+    // pose.  The kernel runs in its one-frame mode.  The caller's rows are then produced by two engines at once, because
+    // either alone is the bottleneck (PCIe at ~55 GB/s for 128-byte rows; the host cores' stores for the expansion):
+    //  * envs [0, nd): complete rows are put together on the device (history_rows_kernel) and DMA-ed straight into the
+    //    caller's buffer (when it is page-locked);
+    //  * envs [nd, N): a kernel turns the frames into 16-byte records + a stream of changed values (~20 bytes per
+    //    env-step instead of 64 + 5) and host threads rebuild the rows -- reset observations included;
+    // chunk by chunk, while later chunks are still being computed.  nd follows the measured balance of the two.
     const bool frames_only = h->cfg.history == 2 && host_obs != nullptr;
+    int nd = 0;                                                      // envs [0, nd) by DMA (frames_only)
+    bool adaptive = false;
     if (K > h->stage_K) {
         cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done);
         h->d_act = nullptr; h->d_obs = nullptr; h->d_rew = nullptr; h->d_done = nullptr; h->stage_K = 0;
@@ -612,24 +632,32 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     cudaStream_t s = (cudaStream_t)stream;
     if (!h->copy_stream) {
         CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-        for (auto &ev : h->chunk_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        for (auto &ev : h->copy_done) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        const unsigned evf = std::getenv("SHIPSIM_HOST_TRACE") ? cudaEventDefault : cudaEventDisableTiming;
+        for (auto &ev : h->chunk_done) CU(cudaEventCreateWithFlags(&ev, evf));
+        for (auto &ev : h->copy_done) CU(cudaEventCreateWithFlags(&ev, evf));
+        CU(cudaEventCreateWithFlags(&h->trace0, evf));
+        CU(cudaStreamCreateWithFlags(&h->aux_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->act_up, cudaEventDisableTiming));
+        if (std::getenv("SHIPSIM_HOST_TRACE")) for (auto &ev : h->trace_mid) CU(cudaEventCreate(&ev));
     }
     int n_chunks = K >= 64 ? 16 : (K >= 8 ? 8 : 1);
     if (const char *ev = std::getenv("SHIPSIM_HOST_CHUNKS")) n_chunks = std::max(1, std::min({atoi(ev), (int)shipsim_handle::kMaxChunks, (int)K}));
     int kbeg[shipsim_handle::kMaxChunks + 1];
     for (int c = 0; c <= n_chunks; ++c) kbeg[c] = (int)((int64_t)K * c / n_chunks);
     const size_t nblk = (N + 31) / 32;
+    for (int c = 0; c < n_chunks; ++c)
+        if (kbeg[c + 1] <= kbeg[c]) return fail(SHIPSIM_ERR_ARG, "internal: empty chunk");
     if (frames_only) {
-        // Value stream: 8 floats per env-step of capacity (measured need on the default map: 0.9); a chunk that needs
-        // more -- it cannot happen with fewer than 8 of 12 slots changing on average -- is sent as plain frames instead.
-        h->var_per_step = 8;
+        // Value stream: room for all 12 variable slots of every env-step (measured need on the default map: 0.9), so
+        // that it cannot overflow; untouched pages of the mapping cost nothing.
+        h->var_per_step = 12;
         if (n > h->rec_cap) {
             cudaFree(h->d_rec); cudaFree(h->d_off); cudaFree(h->d_count);
             if (h->h_rec) cudaFreeHost(h->h_rec);
             if (h->h_off) cudaFreeHost(h->h_off);
             if (h->h_count) cudaFreeHost(h->h_count);
             if (h->h_var) cudaFreeHost(h->h_var);
+            cudaFree(h->d_var); h->d_var = nullptr;
             h->d_rec = nullptr; h->d_off = nullptr; h->d_count = nullptr; h->h_rec = nullptr; h->h_off = nullptr; h->h_count = nullptr;
             h->h_var = nullptr; h->rec_cap = 0;
             CU(cudaMalloc(&h->d_rec, n * sizeof(uint4)));
@@ -638,7 +666,8 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
             CU(cudaHostAlloc(&h->h_rec, n * sizeof(uint4), cudaHostAllocDefault));
             CU(cudaHostAlloc(&h->h_off, (size_t)K * nblk * sizeof(unsigned), cudaHostAllocDefault));
             CU(cudaHostAlloc(&h->h_count, shipsim_handle::kMaxChunks * sizeof(unsigned), cudaHostAllocDefault));
-            CU(cudaHostAlloc(&h->h_var, n * h->var_per_step * sizeof(float), cudaHostAllocMapped));
+            CU(cudaHostAlloc(&h->h_var, n * h->var_per_step * sizeof(float), cudaHostAllocDefault));
+            CU(cudaMalloc(&h->d_var, n * h->var_per_step * sizeof(float)));
             h->rec_cap = n;
         }
         if (N > h->cur_cap) {
@@ -646,14 +675,6 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
             h->h_cur = nullptr; h->cur_cap = 0;
             CU(cudaHostAlloc(&h->h_cur, N * kFrame * sizeof(float), cudaHostAllocDefault));
             h->cur_cap = N;
-        }
-        // fallback staging (plain frames), sized for one chunk
-        const size_t need = (size_t)(kbeg[1] - kbeg[0] + 1) * N * kFrame + N * kFrame;
-        if (need > h->h_frames_cap) {
-            if (h->h_frames) cudaFreeHost(h->h_frames);
-            h->h_frames = nullptr; h->h_frames_cap = 0;
-            CU(cudaHostAlloc(&h->h_frames, need * sizeof(float), cudaHostAllocDefault));
-            h->h_frames_cap = need;
         }
         if (!h->d_frame0) CU(cudaMalloc(&h->d_frame0, N * kFrame * sizeof(float)));
         if (!h->pool) {
@@ -665,95 +686,226 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
         CU(launch_frame(h->p, h->d_frame0, s));
         CU(cudaMemsetAsync(h->d_count, 0, shipsim_handle::kMaxChunks * sizeof(unsigned), s));
         h->launches++;
+        // how many envs travel as complete rows
+        cudaPointerAttributes attr{};
+        const bool pinned = cudaPointerGetAttributes(&attr, host_obs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const char *fixed = std::getenv("SHIPSIM_HOST_DMA_ENVS");
+        if (!pinned) nd = 0;
+        else if (fixed) nd = std::max(0, std::min(atoi(fixed), (int)N));
+        else if (n < ((size_t)1 << 18)) nd = 0;                       // (small calls are latency bound either way)
+        else {
+            adaptive = true;
+            if (h->dma_envs < 0 || h->dma_for_n != (int)N || h->dma_for_k != K) {
+                // First guess.  With a core per ~4 GB/s of rows the host threads alone are the faster engine, and DMA
+                // writes landing next to their streaming stores slow both (B200 box, 16 cores: 6.4 ms per 4,096 x 1,000
+                // call with the host threads alone, 8-10 ms with any share by DMA; profiles/r02_e2e_sweep.log); with few
+                // cores per GPU the copy engine has to carry most of it.
+                const int thr = h->pool->size();
+                h->dma_envs = thr >= 8 ? 0 : (int)((double)N * 50.0 / (50.0 + 9.0 * thr));
+                h->dma_for_n = (int)N; h->dma_for_k = K;
+                h->dma_step = std::max(32, (int)(N / 8) / 32 * 32);
+                h->dma_dir = 1;
+                h->dma_last_t = 0.0;
+            }
+            nd = h->dma_envs;
+        }
+        nd = nd >= (int)N ? (int)N : (nd / 32) * 32;
+        if ((size_t)nd * K > h->rows_cap) {
+            cudaFree(h->d_rows);
+            h->d_rows = nullptr; h->rows_cap = 0;
+            CU(cudaMalloc(&h->d_rows, (size_t)nd * K * 2 * kFrame * sizeof(float)));
+            h->rows_cap = (size_t)nd * K;
+        }
     }
-    CU(cudaMemcpyAsync(h->d_act, host_actions, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    h->last_h2d = (int64_t)(n * sizeof(int32_t));
+    const bool trace = std::getenv("SHIPSIM_HOST_TRACE") != nullptr;
+    if (trace) CU(cudaEventRecord(h->trace0, s));
+    h->last_h2d = (int64_t)(n * sizeof(int32_t));                   // (the actions go up chunk by chunk, ahead of the chunk's kernel)
     h->last_d2h = 0;
     // The rollout is cut into chunks of steps: while chunk i+1 is being computed on the caller's stream, the results
     // of chunk i travel to the host on the copy stream and chunk i-1 is being expanded by the host threads.
     const size_t row_full = (size_t)kFrame * h->cfg.history;        // floats per complete row; chunk regions of d_obs are sized for it
-    float *d_var = nullptr;
-    if (frames_only) CU(cudaHostGetDevicePointer((void **)&d_var, h->h_var, 0));
-    const float4 *prev_frames = h->d_frame0;                        // the frames the next chunk's first step is compared with
-    for (int c = 0; c < n_chunks; ++c) {
-        const int k0 = kbeg[c], kc = kbeg[c + 1] - kbeg[c];
-        if (kc <= 0) continue;
-        const size_t off = (size_t)k0 * N;
-        const int hist_c = frames_only ? 1 : h->cfg.history;
-        float *d_chunk = h->d_obs + off * row_full;
-        const int rc2 = step_impl(h, h->d_act + off, SHIPSIM_ACTION_I32, kc, d_chunk, h->d_rew + off, h->d_done + off, stream, hist_c);
-        if (rc2) return rc2;
-        if (frames_only) {
-            CU(launch_compact_frames((const float4 *)d_chunk, prev_frames, h->d_rew + off, h->d_done + off, (int)N, kc, h->cfg.step_penalty,
-                                     h->d_rec + off, h->d_off + (size_t)k0 * nblk, d_var + off * h->var_per_step,
-                                     (unsigned)std::min<size_t>((size_t)kc * N * h->var_per_step, 0xffffffffu), h->d_count + c, s));
-            h->launches++;
-            prev_frames = (const float4 *)d_chunk + ((size_t)(kc - 1) * N) * 4;
-        }
-        CU(cudaEventRecord(h->chunk_done[c], s));
-        CU(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
-        if (frames_only) {
-            if (c == 0) {
-                CU(cudaMemcpyAsync(h->h_cur, h->d_frame0, N * kFrame * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-                h->last_d2h += (int64_t)(N * kFrame * sizeof(float));
+    float *d_var = h->d_var;
+    if (const char *ev = std::getenv("SHIPSIM_HOST_VAR_DENSITY")) h->var_density = atof(ev);      // (test hook: 0 forces the fetch-the-rest path)
+    size_t spec[shipsim_handle::kMaxChunks] = {};                    // floats of each chunk's value stream copied down unasked
+    // Every host thread owns a contiguous range of env blocks for the whole call (the running frames of its envs stay in its
+    // cache) and walks the chunks as their records arrive: no barrier between chunks.  Whoever finds the next chunk missing
+    // polls its event.  The threads are started BEFORE the stream work is issued (launching 16 chunks of kernels and copies
+    // takes the calling thread ~1 ms, a fifth of the call), and the calling thread joins them when it is done.
+    const bool expand = frames_only && nd < (int)N;
+    const bool cut = h->cfg.auto_reset != 0;
+    const size_t blk0 = (size_t)nd / 32;
+    const int jobs = expand ? (int)std::min<size_t>(nblk - blk0, (size_t)h->pool->size()) : 0;
+    std::atomic<int> ready{0};                                       // chunks whose records are in host memory
+    std::atomic<int> issued{0};                                      // chunks whose copies (and event) are in the copy stream
+    std::atomic<int> bad{0};
+    std::mutex poll, fix;
+    bool fixed[shipsim_handle::kMaxChunks] = {};
+    std::atomic<long long> extra_d2h{0};
+    const int dev = h->device;
+    const std::function<void(int)> worker = [&](int j) {
+        cudaSetDevice(dev);
+        const size_t b0 = blk0 + (nblk - blk0) * (size_t)j / jobs, b1 = blk0 + (nblk - blk0) * (size_t)(j + 1) / jobs;
+        for (int c = 0; c < n_chunks; ++c) {
+            while (ready.load(std::memory_order_acquire) <= c) {
+                if (bad.load(std::memory_order_relaxed)) return;
+                if (poll.try_lock()) {
+                    const int r = ready.load(std::memory_order_relaxed);
+                    if (r <= c && r < issued.load(std::memory_order_acquire)) {      // (an event not yet recorded by this call reads as complete)
+                        const cudaError_t q = cudaEventQuery(h->copy_done[r]);
+                        if (q == cudaSuccess) ready.store(r + 1, std::memory_order_release);
+                        else if (q != cudaErrorNotReady) bad.store((int)q);
+                    }
+                    poll.unlock();
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
             }
-            CU(cudaMemcpyAsync(h->h_rec + off * 4, h->d_rec + off, (size_t)kc * N * sizeof(uint4), cudaMemcpyDeviceToHost, h->copy_stream));
-            CU(cudaMemcpyAsync(h->h_off + (size_t)k0 * nblk, h->d_off + (size_t)k0 * nblk, (size_t)kc * nblk * sizeof(unsigned),
-                               cudaMemcpyDeviceToHost, h->copy_stream));
-            CU(cudaMemcpyAsync(h->h_count + c, h->d_count + c, sizeof(unsigned), cudaMemcpyDeviceToHost, h->copy_stream));
-            h->last_d2h += (int64_t)kc * N * sizeof(uint4) + (int64_t)kc * nblk * sizeof(unsigned) + sizeof(unsigned);
-        } else {
-            h->last_d2h += (int64_t)kc * N * ((host_reward ? 4 : 0) + (host_done ? 1 : 0));
-            if (host_obs) {
-                h->last_d2h += (int64_t)kc * N * row_full * sizeof(float);
-                CU(cudaMemcpyAsync(host_obs + off * row_full, d_chunk, (size_t)kc * N * row_full * sizeof(float), cudaMemcpyDeviceToHost,
-                                   h->copy_stream));
+            const int k0 = kbeg[c], kc = kbeg[c + 1] - kbeg[c];
+            const size_t off = (size_t)k0 * N;
+            if (h->h_count[c] > spec[c]) {                       // the speculative copy fell short: one thread fetches the rest
+                std::lock_guard<std::mutex> lk(fix);
+                if (!fixed[c]) {
+                    const size_t at = off * h->var_per_step + spec[c];
+                    cudaError_t q = cudaMemcpyAsync(h->h_var + at, d_var + at, (h->h_count[c] - spec[c]) * sizeof(float), cudaMemcpyDeviceToHost,
+                                                    h->aux_stream);
+                    if (q == cudaSuccess) q = cudaStreamSynchronize(h->aux_stream);
+                    if (q != cudaSuccess) { bad.store((int)q); return; }
+                    extra_d2h.fetch_add((long long)(h->h_count[c] - spec[c]) * (long long)sizeof(float));
+                    fixed[c] = true;
+                }
             }
-            if (host_reward) CU(cudaMemcpyAsync(host_reward + off, h->d_rew + off, (size_t)kc * N * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-            if (host_done) CU(cudaMemcpyAsync(host_done + off, h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, h->copy_stream));
+            expand_delta_rows(host_obs + off * row_full, host_reward ? host_reward + off : nullptr, host_done ? host_done + off : nullptr,
+                              h->h_rec + off * 4, h->h_off + (size_t)k0 * nblk, h->h_var + off * h->var_per_step, h->h_cur, kc, N, b0, b1,
+                              h->cfg.step_penalty, cut, 2);
         }
-        CU(cudaEventRecord(h->copy_done[c], h->copy_stream));
-    }
-    if (frames_only) {
-        const bool cut = h->cfg.auto_reset != 0;
-        const int workers = h->pool->size();
+    };
+    using clk = std::chrono::steady_clock;
+    const auto t_begin = clk::now();
+    if (expand) h->pool->start(jobs, worker);
+    const int rc_issue = [&]() -> int {
+        const float4 *prev_frames = h->d_frame0;                        // the frames the next chunk's first step is compared with
         for (int c = 0; c < n_chunks; ++c) {
             const int k0 = kbeg[c], kc = kbeg[c + 1] - kbeg[c];
             if (kc <= 0) continue;
-            CU(cudaEventSynchronize(h->copy_done[c]));
             const size_t off = (size_t)k0 * N;
-            const size_t cap = (size_t)kc * N * h->var_per_step;
-            const unsigned count = h->h_count[c];
-            h->last_d2h += (int64_t)std::min<size_t>(count, cap) * sizeof(float);      // the value stream crossed PCIe too (zero-copy writes)
-            if (count > cap) {
-                // (never seen: more than 8 of 12 slots changing on average.)  This chunk goes home as plain frames.
-                const float *d_chunk = h->d_obs + off * row_full;
-                float *fr = h->h_frames;
-                std::memcpy(fr, h->h_cur, N * kFrame * sizeof(float));
-                CU(cudaMemcpyAsync(fr + N * kFrame, d_chunk, (size_t)kc * N * kFrame * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-                std::vector<uint8_t> dn((size_t)kc * N);
-                CU(cudaMemcpyAsync(dn.data(), h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, h->copy_stream));
-                if (host_reward) CU(cudaMemcpyAsync(host_reward + off, h->d_rew + off, (size_t)kc * N * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-                CU(cudaStreamSynchronize(h->copy_stream));
-                h->last_d2h += (int64_t)kc * N * (kFrame * sizeof(float) + 5);
-                assemble_history_rows(host_obs + off * row_full, fr, cut ? dn.data() : nullptr, 0, (size_t)kc * N, N);
-                if (host_done) std::memcpy(host_done + off, dn.data(), (size_t)kc * N);
-                std::memcpy(h->h_cur, fr + (size_t)kc * N * kFrame, N * kFrame * sizeof(float));
-                continue;
+            const int hist_c = frames_only ? 1 : h->cfg.history;
+            float *d_chunk = h->d_obs + off * row_full;
+            if (c == 0) {
+                // the first chunk's actions go up ahead of its kernel; the rest follows on another stream while it runs
+                CU(cudaMemcpyAsync(h->d_act, host_actions, (size_t)kc * N * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+                if (n_chunks > 1) {
+                    CU(cudaEventRecord(h->act_up, s));                   // (orders the copy behind whatever the caller's stream did before)
+                    CU(cudaStreamWaitEvent(h->aux_stream, h->act_up, 0));
+                    CU(cudaMemcpyAsync(h->d_act + (size_t)kc * N, host_actions + (size_t)kc * N, (n - (size_t)kc * N) * sizeof(int32_t),
+                                       cudaMemcpyHostToDevice, h->aux_stream));
+                    CU(cudaEventRecord(h->act_up, h->aux_stream));
+                }
+            } else if (c == 1) CU(cudaStreamWaitEvent(s, h->act_up, 0));
+            const int rc2 = step_impl(h, h->d_act + off, SHIPSIM_ACTION_I32, kc, d_chunk, h->d_rew + off, h->d_done + off, stream, hist_c);
+            if (rc2) return rc2;
+            if (trace) CU(cudaEventRecord(h->trace_mid[c], s));
+            if (frames_only) {
+                if (nd < (int)N) {
+                    CU(launch_compact_frames((const float4 *)d_chunk, prev_frames, h->d_rew + off, h->d_done + off, (int)N, nd, kc, h->cfg.step_penalty,
+                                             h->d_rec + off, h->d_off + (size_t)k0 * nblk, d_var + off * h->var_per_step,
+                                             (unsigned)std::min<size_t>((size_t)kc * N * h->var_per_step, 0xffffffffu), h->d_count + c, s));
+                    h->launches++;
+                }
+                if (nd > 0) {
+                    CU(launch_history_rows((const float4 *)d_chunk, prev_frames, h->d_done + off, (int)N, nd, kc, h->cfg.auto_reset != 0,
+                                           (float4 *)(h->d_rows + (size_t)k0 * nd * row_full), s));
+                    h->launches++;
+                }
+                prev_frames = (const float4 *)d_chunk + ((size_t)(kc - 1) * N) * 4;
             }
-            // env blocks are dealt out in contiguous ranges: a worker walks the chunk's steps over its own envs, whose
-            // running frames stay in its cache
-            const int jobs = (int)std::min<size_t>(nblk, (size_t)workers * 4);
-            h->pool->run(jobs, [&](int j) {
-                const size_t b0 = nblk * (size_t)j / jobs, b1 = nblk * (size_t)(j + 1) / jobs;
-                expand_delta_rows(host_obs + off * row_full, host_reward ? host_reward + off : nullptr, host_done ? host_done + off : nullptr,
-                                  h->h_rec + off * 4, h->h_off + (size_t)k0 * nblk, h->h_var + off * h->var_per_step, h->h_cur, kc, N, b0, b1,
-                                  h->cfg.step_penalty, cut, 2);
-            });
+            CU(cudaEventRecord(h->chunk_done[c], s));
+            CU(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+            if (frames_only) {
+                if (nd < (int)N) {
+                    if (c == 0) {
+                        CU(cudaMemcpyAsync(h->h_cur, h->d_frame0, N * kFrame * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+                        h->last_d2h += (int64_t)(N * kFrame * sizeof(float));
+                    }
+                    if (nd == 0) CU(cudaMemcpyAsync(h->h_rec + off * 4, h->d_rec + off, (size_t)kc * N * sizeof(uint4), cudaMemcpyDeviceToHost, h->copy_stream));
+                    else CU(cudaMemcpy2DAsync(h->h_rec + (off + nd) * 4, N * sizeof(uint4), h->d_rec + off + nd, N * sizeof(uint4), (N - nd) * sizeof(uint4),
+                                              kc, cudaMemcpyDeviceToHost, h->copy_stream));
+                    CU(cudaMemcpyAsync(h->h_off + (size_t)k0 * nblk, h->d_off + (size_t)k0 * nblk, (size_t)kc * nblk * sizeof(unsigned),
+                                       cudaMemcpyDeviceToHost, h->copy_stream));
+                    CU(cudaMemcpyAsync(h->h_count + c, h->d_count + c, sizeof(unsigned), cudaMemcpyDeviceToHost, h->copy_stream));
+                    // the values: how many there are is only known on the device, so a size that has been enough so far goes
+                    // down unasked (a host thread fetches the rest in the rare case that it was not)
+                    spec[c] = std::min((size_t)kc * N * h->var_per_step, (size_t)((double)kc * (N - nd) * h->var_density) + 1024);
+                    CU(cudaMemcpyAsync(h->h_var + off * h->var_per_step, d_var + off * h->var_per_step, spec[c] * sizeof(float),
+                                       cudaMemcpyDeviceToHost, h->copy_stream));
+                    h->last_d2h += (int64_t)kc * (N - nd) * sizeof(uint4) + (int64_t)kc * nblk * sizeof(unsigned) + sizeof(unsigned)
+                                   + (int64_t)spec[c] * sizeof(float);
+                }
+                CU(cudaEventRecord(h->copy_done[c], h->copy_stream));       // what the host threads wait for
+                issued.store(c + 1, std::memory_order_release);
+                if (nd > 0) {
+                    const size_t w = (size_t)nd * row_full * sizeof(float);
+                    CU(cudaMemcpy2DAsync(host_obs + off * row_full, N * row_full * sizeof(float), h->d_rows + (size_t)k0 * nd * row_full, w, w, kc,
+                                         cudaMemcpyDeviceToHost, h->copy_stream));
+                    if (host_reward) CU(cudaMemcpy2DAsync(host_reward + off, N * sizeof(float), h->d_rew + off, N * sizeof(float), nd * sizeof(float), kc,
+                                                          cudaMemcpyDeviceToHost, h->copy_stream));
+                    if (host_done) CU(cudaMemcpy2DAsync(host_done + off, N, h->d_done + off, N, nd, kc, cudaMemcpyDeviceToHost, h->copy_stream));
+                    h->last_d2h += (int64_t)kc * nd * (row_full * sizeof(float) + (host_reward ? 4 : 0) + (host_done ? 1 : 0));
+                }
+                continue;
+            } else {
+                h->last_d2h += (int64_t)kc * N * ((host_reward ? 4 : 0) + (host_done ? 1 : 0));
+                if (host_obs) {
+                    h->last_d2h += (int64_t)kc * N * row_full * sizeof(float);
+                    CU(cudaMemcpyAsync(host_obs + off * row_full, d_chunk, (size_t)kc * N * row_full * sizeof(float), cudaMemcpyDeviceToHost,
+                                       h->copy_stream));
+                }
+                if (host_reward) CU(cudaMemcpyAsync(host_reward + off, h->d_rew + off, (size_t)kc * N * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+                if (host_done) CU(cudaMemcpyAsync(host_done + off, h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, h->copy_stream));
+            }
+            CU(cudaEventRecord(h->copy_done[c], h->copy_stream));
         }
+        return SHIPSIM_OK;
+    }();
+    if (expand) {
+        if (rc_issue) bad.store(-1);
+        h->pool->finish();
+    }
+    if (rc_issue) return rc_issue;
+    if (expand) {
+        if (bad.load()) return fail(SHIPSIM_ERR_CUDA, std::string("copy stream: ") + cudaGetErrorString((cudaError_t)bad.load()));
+        h->last_d2h += extra_d2h.load();
+        double dens = 0.0;
+        for (int c = 0; c < n_chunks; ++c) dens = std::max(dens, (double)h->h_count[c] / ((double)(kbeg[c + 1] - kbeg[c]) * (double)(N - nd)));
+        h->var_density = std::max(0.9 * h->var_density, std::min(12.0, 1.25 * dens + 0.25));       // follows the need up at once, down slowly
     }
     CU(cudaStreamSynchronize(h->copy_stream));
     CU(cudaStreamSynchronize(s));
+    if (trace) {
+        std::fprintf(stderr, "step_host trace (ms since the call's first stream op): host done %.2f\n",
+                     std::chrono::duration<double, std::milli>(clk::now() - t_begin).count());
+        for (int c = 0; c < n_chunks; ++c) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, h->trace0, h->chunk_done[c]);
+            cudaEventElapsedTime(&b, h->trace0, h->copy_done[c]);
+            float m = 0.f;
+            cudaEventElapsedTime(&m, h->trace0, h->trace_mid[c]);
+            std::fprintf(stderr, "  chunk %2d: step kernel done %.2f  compaction done %.2f  records home %.2f\n", c, m, a, b);
+        }
+    }
+    if (adaptive) {
+        // The split for the next call climbs towards the shorter call: keep going while the time per env-step improves, turn
+        // round (with half the step) when it gets worse, stay when it no longer changes.
+        const double t = std::chrono::duration<double>(clk::now() - t_begin).count() / (double)n;
+        if (h->dma_last_t > 0.0 && t > h->dma_last_t * 1.015) {
+            h->dma_dir = -h->dma_dir;
+            h->dma_step = std::max(32, h->dma_step / 2 / 32 * 32);
+        }
+        if (h->dma_last_t == 0.0 || t < h->dma_last_t * 0.985 || t > h->dma_last_t * 1.015)
+            h->dma_envs = std::max(0, std::min((int)N, nd + h->dma_dir * h->dma_step));
+        h->dma_last_t = t;
+    }
     return SHIPSIM_OK;
 }
 

@@ -69,10 +69,7 @@ void assemble_history_rows(float *obs, const float *frames, const uint8_t *cut, 
 // ---------------------------------------------------------------------------------------------------------------------
 static inline float bits_f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
-template <int LEVEL>        // 0 plain, 1 SSE2, 2 AVX-512 (callers guarantee the alignment the level needs)
-#if defined(__x86_64__)
-__attribute__((target("avx512f")))
-#endif
+template <int LEVEL>        // 0 plain, 1 SSE2 (callers guarantee the alignment the level needs)
 static void expand_rows_impl(float *obs, float *rew, uint8_t *done, const uint32_t *rec, const uint32_t *off, const float *var, float *cur,
                              int kc, size_t N, size_t blk_begin, size_t blk_end, float step_penalty, bool cut_on_done, int history)
 {
@@ -93,8 +90,7 @@ static void expand_rows_impl(float *obs, float *rew, uint8_t *done, const uint32
                 if (dst && history == 2) {                      // the previous frame goes out before it is overwritten
                     const bool reset_row = cut_on_done && dn;
 #if defined(__x86_64__)
-                    if (LEVEL == 2) _mm512_stream_ps(dst, reset_row ? _mm512_set1_ps(-1.f) : _mm512_load_ps(c));
-                    else if (LEVEL == 1) for (int i = 0; i < kF; i += 4) _mm_stream_ps(dst + i, reset_row ? _mm_set1_ps(-1.f) : _mm_load_ps(c + i));
+                    if (LEVEL == 1) for (int i = 0; i < kF; i += 4) _mm_stream_ps(dst + i, reset_row ? _mm_set1_ps(-1.f) : _mm_load_ps(c + i));
                     else
 #endif
                     { if (reset_row) for (int i = 0; i < kF; ++i) dst[i] = -1.f; else std::memcpy(dst, c, kF * sizeof(float)); }
@@ -105,8 +101,7 @@ static void expand_rows_impl(float *obs, float *rew, uint8_t *done, const uint32
                 for (uint32_t m = (word >> 8) & 0xfffu; m; m &= m - 1u) c[4 + __builtin_ctz(m)] = *v++;
                 if (dst) {
 #if defined(__x86_64__)
-                    if (LEVEL == 2) _mm512_stream_ps(dst, _mm512_load_ps(c));
-                    else if (LEVEL == 1) for (int i = 0; i < kF; i += 4) _mm_stream_ps(dst + i, _mm_load_ps(c + i));
+                    if (LEVEL == 1) for (int i = 0; i < kF; i += 4) _mm_stream_ps(dst + i, _mm_load_ps(c + i));
                     else
 #endif
                     std::memcpy(dst, c, kF * sizeof(float));
@@ -121,6 +116,52 @@ static void expand_rows_impl(float *obs, float *rew, uint8_t *done, const uint32
 #endif
 }
 
+#if defined(__x86_64__)
+// AVX-512: the frame is one register.  Slots 4..15 take the changed values straight from the stream with an expanding
+// load under the change mask (vexpandps), slots 0..3 come from the record; two streaming stores per row.
+__attribute__((target("avx512f"))) static void expand_rows_avx512(float *obs, float *rew, uint8_t *done, const uint32_t *rec,
+                                                                  const uint32_t *off, const float *var, float *cur, int kc, size_t N,
+                                                                  size_t blk_begin, size_t blk_end, float step_penalty, bool cut_on_done,
+                                                                  int history)
+{
+    const size_t nblk = (N + 31) / 32;
+    const float rtab[4] = {step_penalty, 1.f, -1.f, 0.f};
+    alignas(32) static const float rudtab[8] = {-10.f, -5.f, 0.f, 5.f, 10.f, 15.f, 20.f, 25.f};
+    const __m512 neg = _mm512_set1_ps(-1.f);
+    const int row_f = kF * history;
+    for (int k = 0; k < kc; ++k) {
+        for (size_t blk = blk_begin; blk < blk_end; ++blk) {
+            const float *v = var + off[(size_t)k * nblk + blk];
+            const size_t e1 = std::min(N, blk * 32 + 32);
+            for (size_t e = blk * 32; e < e1; ++e) {
+                const size_t row = (size_t)k * N + e;
+                const __m128i q = _mm_loadu_si128((const __m128i *)(rec + row * 4));
+                const uint32_t word = (uint32_t)_mm_extract_epi32(q, 3);
+                const bool dn = (word >> 5) & 1u;
+                float *c = cur + e * kF;
+                __m512 f = _mm512_load_ps(c);
+                float *dst = obs ? obs + row * row_f : nullptr;
+                if (dst && history == 2) {
+                    _mm512_stream_ps(dst, cut_on_done && dn ? neg : f);
+                    dst += kF;
+                }
+                __m128 head = _mm_castsi128_ps(_mm_shuffle_epi32(q, _MM_SHUFFLE(2, 2, 1, 0)));      // x, y, angle, angle
+                head = _mm_insert_ps(head, _mm_load_ss(rudtab + (word & 7u)), 0x20);                // x, y, rudder, angle
+                const __mmask16 m = (__mmask16)(((word >> 8) & 0xfffu) << 4);
+                f = _mm512_mask_expandloadu_ps(f, m, v);
+                f = _mm512_insertf32x4(f, head, 0);
+                v += __builtin_popcount(m);
+                _mm512_store_ps(c, f);
+                if (dst) _mm512_stream_ps(dst, f);
+                if (rew) rew[row] = rtab[(word >> 3) & 3u];
+                if (done) done[row] = dn ? 1 : 0;
+            }
+        }
+    }
+    _mm_sfence();
+}
+#endif
+
 void expand_delta_rows(float *obs, float *rew, uint8_t *done, const uint32_t *rec, const uint32_t *off, const float *var, float *cur,
                        int kc, size_t N, size_t blk_begin, size_t blk_end, float step_penalty, bool cut_on_done, int history)
 {
@@ -128,7 +169,7 @@ void expand_delta_rows(float *obs, float *rew, uint8_t *done, const uint32_t *re
     static const int level = __builtin_cpu_supports("avx512f") ? 2 : 1;
     const uintptr_t al = (uintptr_t)obs | (uintptr_t)cur;
     if ((al & 63) == 0 && level == 2)
-        return expand_rows_impl<2>(obs, rew, done, rec, off, var, cur, kc, N, blk_begin, blk_end, step_penalty, cut_on_done, history);
+        return expand_rows_avx512(obs, rew, done, rec, off, var, cur, kc, N, blk_begin, blk_end, step_penalty, cut_on_done, history);
     if ((al & 15) == 0)
         return expand_rows_impl<1>(obs, rew, done, rec, off, var, cur, kc, N, blk_begin, blk_end, step_penalty, cut_on_done, history);
 #endif

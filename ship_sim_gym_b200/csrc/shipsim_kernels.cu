@@ -656,17 +656,18 @@ __global__ void __launch_bounds__(256) frame_kernel(const __grid_constant__ Step
 // (change mask: bit j set <=> slot 4 + j of the frame -- gx, gy, lidar 0..9 -- differs bitwise from the env's previous
 // frame) and appends the changed values to a variable-length stream; off[k][block] = where the values of the 32 envs
 // of a block start at step k (the blocks' order in the stream is whatever the atomics made it: the table is the truth).
-// One warp per (step, 32-env block).  The host rebuilds the frames exactly (shipsim_host.cpp: expand_delta_rows).
+// One warp per (step, 32-env block), blocks blk0 and up (the envs below 32 * blk0 go home as complete rows by DMA:
+// history_rows_kernel).  The host rebuilds the frames exactly (shipsim_host.cpp: expand_delta_rows).
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) compact_frames_kernel(const float4 *frames, const float4 *prev0, const float *rew, const uint8_t *done,
-                                                             int N, int kc, float step_penalty, uint4 *rec, unsigned *off, float *var,
+                                                             int N, int blk0, int kc, float step_penalty, uint4 *rec, unsigned *off, float *var,
                                                              unsigned var_cap, unsigned *counter)
 {
     const int lane = threadIdx.x & 31;
-    const int nblk = (N + 31) / 32;
+    const int nblk = (N + 31) / 32, nb = nblk - blk0;
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (w >= (long long)kc * nblk) return;
-    const int k = (int)(w / nblk), blk = (int)(w % nblk);
+    if (w >= (long long)kc * nb) return;
+    const int k = (int)(w / nb), blk = blk0 + (int)(w % nb);
     const int e = blk * 32 + lane;
     const bool valid = e < N;
     unsigned mask = 0u;
@@ -712,6 +713,27 @@ __global__ void __launch_bounds__(256) compact_frames_kernel(const float4 *frame
             if (at < var_cap) var[at] = vals[j];        // (beyond the capacity: dropped; the host sees counter > capacity)
             ++at;
         }
+}
+
+// Complete observation rows [previous frame | frame] of the envs [0, nd) for a chunk of frames (ship_env.py:112-113;
+// 16 x -1 as the previous frame of a step that ended an episode under auto-reset, ship_env.py:180-184): the part of the
+// host path's output that travels as plain rows by DMA while the host threads expand the compacted part.  One thread per
+// quarter frame; rows[kc][nd][32].
+__global__ void __launch_bounds__(256) history_rows_kernel(const float4 *frames, const float4 *prev0, const uint8_t *done, int N, int nd,
+                                                           int kc, int cut, float4 *rows)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)kc * nd * 4) return;
+    const int q = (int)(t & 3);
+    const long long ke = t >> 2;
+    const int k = (int)(ke / nd), e = (int)(ke % nd);
+    const size_t at = ((size_t)k * N + e) * 4 + q;
+    const float4 cur = frames[at];
+    float4 prev = k > 0 ? frames[at - (size_t)N * 4] : prev0[(size_t)e * 4 + q];
+    if (cut && done[(size_t)k * N + e]) prev = make_float4(-1.f, -1.f, -1.f, -1.f);
+    float4 *o = rows + (size_t)ke * 8 + q;
+    __stcs(o, prev);
+    __stcs(o + 4, cur);
 }
 
 // stats slots -> out[kStatLen]; one warp per statistic column
@@ -787,13 +809,23 @@ cudaError_t launch_clamp_scenarios(float4 *state, int N, int n_scen, cudaStream_
     return cudaGetLastError();
 }
 
-cudaError_t launch_compact_frames(const float4 *frames, const float4 *prev0, const float *rew, const uint8_t *done, int N, int kc,
+cudaError_t launch_compact_frames(const float4 *frames, const float4 *prev0, const float *rew, const uint8_t *done, int N, int env0, int kc,
                                   float step_penalty, uint4 *rec, unsigned *off, float *var, unsigned var_cap, unsigned *counter,
                                   cudaStream_t stream)
 {
-    const long long warps = (long long)kc * ((N + 31) / 32);
-    compact_frames_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(frames, prev0, rew, done, N, kc, step_penalty, rec, off,
-                                                                                   var, var_cap, counter);
+    const long long warps = (long long)kc * ((N + 31) / 32 - env0 / 32);
+    if (warps <= 0) return cudaSuccess;
+    compact_frames_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(frames, prev0, rew, done, N, env0 / 32, kc, step_penalty,
+                                                                                   rec, off, var, var_cap, counter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_history_rows(const float4 *frames, const float4 *prev0, const uint8_t *done, int N, int nd, int kc, int cut, float4 *rows,
+                                cudaStream_t stream)
+{
+    const long long threads = (long long)kc * nd * 4;
+    if (threads <= 0) return cudaSuccess;
+    history_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(frames, prev0, done, N, nd, kc, cut, rows);
     return cudaGetLastError();
 }
 

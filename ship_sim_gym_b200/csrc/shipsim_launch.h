@@ -25,9 +25,11 @@ cudaError_t launch_pack_bank(double *hull_xy, const int *hull_n, const double *g
                              EdgeD *edges, cudaStream_t stream);
 cudaError_t launch_max_hull(const int *hull_n, int n, int *out, cudaStream_t stream);
 cudaError_t launch_clamp_scenarios(float4 *state, int N, int n_scen, cudaStream_t stream);
-cudaError_t launch_compact_frames(const float4 *frames, const float4 *prev0, const float *rew, const uint8_t *done, int N, int kc,
+cudaError_t launch_compact_frames(const float4 *frames, const float4 *prev0, const float *rew, const uint8_t *done, int N, int env0, int kc,
                                   float step_penalty, uint4 *rec, unsigned *off, float *var, unsigned var_cap, unsigned *counter,
                                   cudaStream_t stream);
+cudaError_t launch_history_rows(const float4 *frames, const float4 *prev0, const uint8_t *done, int N, int nd, int kc, int cut, float4 *rows,
+                                cudaStream_t stream);
 cudaError_t launch_frame(const StepParams &p, float4 *out, cudaStream_t stream);
 cudaError_t launch_render(const StepParams &p, int e, int img_w, int img_h, uint8_t *rgb, cudaStream_t stream);
 cudaError_t launch_stats_reduce(double *slots, double *out, int clear, cudaStream_t stream);

@@ -324,3 +324,39 @@ def test_host_path_rebuilds_history_from_frames(auto_reset, n, K):
         assert np.array_equal(ho, o), "call %d" % it
         if auto_reset and K >= 100:
             assert d.sum() > 0
+
+
+@pytest.mark.parametrize("dma_envs", ["0", "96", "512", "1000", None])
+def test_host_path_two_engine_split(dma_envs, monkeypatch):
+    """shipsim_step_host with page-locked caller buffers: the envs [0, nd) come home as complete rows by DMA
+    (history_rows_kernel), the others compacted and expanded by the host threads.  Every split -- none, ragged, all, and
+    the self-balancing one over consecutive calls -- gives the rows, rewards and done flags of the device-resident rollout,
+    bit for bit."""
+    from ship_sim_gym_b200 import BatchedShipEnv, ScenarioBank
+    if dma_envs is None:
+        monkeypatch.delenv("SHIPSIM_HOST_DMA_ENVS", raising=False)
+    else:
+        monkeypatch.setenv("SHIPSIM_HOST_DMA_ENVS", dma_envs)
+    if dma_envs == "96":          # the speculative copy of the changed values falls short: a host thread fetches the rest
+        monkeypatch.setenv("SHIPSIM_HOST_VAR_DENSITY", "0")
+    n, K = (1000, 64) if dma_envs is not None else (4096, 80)
+    bank = ScenarioBank.generate(16, (600, 600), seed=2)
+    rng = np.random.RandomState(5)
+    envs = [BatchedShipEnv(n, bank=bank, seed=1, auto_reset=True) for _ in range(2)]
+    for e in envs:
+        e.reset()
+    pin = lambda *s, dtype: torch.empty(*s, dtype=dtype).pin_memory()       # noqa: E731
+    ho, hr, hd = pin(K, n, 32, dtype=torch.float32), pin(K, n, dtype=torch.float32), pin(K, n, dtype=torch.uint8)
+    seen = set()
+    for it in range(6 if dma_envs is None else 2):
+        acts = rng.randint(0, 3, (K, n)).astype(np.int32)
+        o, r, d = [t.cpu().numpy() for t in envs[0].rollout(torch.tensor(acts, device="cuda"))]
+        ho.fill_(7.0)
+        envs[1].step_host(acts, K=K, out=(ho.numpy(), hr.numpy(), hd.numpy()))
+        assert np.array_equal(ho.numpy(), o) and np.array_equal(hr.numpy(), r) and np.array_equal(hd.numpy(), d), "call %d" % it
+        seen.add(envs[1].host_traffic()[1])
+    assert d.sum() > 0
+    if dma_envs is None:
+        assert len(seen) > 1          # the split moved between calls (it follows the measured balance)
+    for e in envs:
+        e.close()
