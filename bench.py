@@ -381,6 +381,8 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = env.launch_info()["launches"] - l0
+    # this rank's statistics as of the last all-reduced rollout (taken before anything else steps the envs)
+    local_stats = env.stats_tensor(clear=False).clone()
     if sampler.nv is not None and sampler.armed_samples() < 5:    # region too short for NVML: extend, untimed
         t_end = time.time() + 0.5
         while time.time() < t_end:          # no collective in here: ranks run different numbers of these
@@ -396,7 +398,6 @@ def main():
 
     # ---- the only collective of the path, checked on the GPUs: the all-reduced vector of the last rollout must equal
     # the sum of the all-gathered per-rank vectors; the printed statistics are the GLOBAL ones
-    local_stats = env.stats_tensor(clear=False).clone()
     collective = None
     if world > 1 and reduce_mode == "full":
         reduced = reducer.latest().clone()

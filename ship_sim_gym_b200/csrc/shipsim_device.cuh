@@ -334,6 +334,19 @@ __device__ __forceinline__ void cp_async16_s(unsigned smem_dst, const void *gmem
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) { cp_async16_s(smem_addr(smem_dst), gmem_src); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// Bulk asynchronous shared -> global copy by the TMA unit (UBLKCP): one instruction moves a contiguous run of shared
+// memory (multiple of 16 bytes, 16-byte aligned at both ends) -- an env's whole observation row -- instead of a loop of
+// 128-bit loads and stores.  Writes made with ordinary st.shared must be fenced into the async proxy first
+// (fence_proxy_async by the writers, then a warp / CTA sync); bulk_store_wait_read returns once the unit has READ the
+// source, i.e. the row may be overwritten.
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void *gmem_dst, unsigned smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // Episode statistics of one step for a whole warp: counters by ballot + popc, the two sums (episode return and length of
 // the envs that finished) by visiting the few finished lanes.  Lane 0 adds the totals to the warp's eight accumulators
 // (shared-space address `stat`): plain shared-memory read-modify-write, no atomics (measured: the shared atomics cost 4 %

@@ -30,6 +30,14 @@
 #ifndef SHIPSIM_BIG_MIN_BLOCKS
 #define SHIPSIM_BIG_MIN_BLOCKS 5
 #endif
+// SHIPSIM_TMA_STORE=1: observation rows leave the SM by TMA bulk copies (one cp.async.bulk.global.shared::cta per env
+// row, fence.proxy.async + bulk wait_group) instead of the loop of 128-bit shared loads + streaming stores.  Correct
+// (the whole GPU suite passes with it) but measured 15-17 % SLOWER (1M envs x 32 steps: 1.68 -> 1.98 ms; hard map 65,536
+// envs: 0.52 -> 0.61 ms; profiles/r02_tma_store_ab.log): a 128-byte row is too small a unit for the TMA engine -- 640
+// bulk operations per SM per step against 8 LDS + 8 STG per lane that issue in the shadow of other warps.  Off.
+#ifndef SHIPSIM_TMA_STORE
+#define SHIPSIM_TMA_STORE 0
+#endif
 
 namespace shipsim {
 
@@ -145,6 +153,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             // the one value the 96-register build spilled -- and a spilled prefetch is a synchronous load)
             const int a = load_action_at(p, (size_t)k * p.N + min(e, p.N - 1), k, p.env_id_offset + e);   // (idle lanes read the last env's)
             // previous frame <- newest frame of the last step / reset (SURVEY.md App. A note N2); lidar stays in place
+            if (SHIPSIM_TMA_STORE && k > 0) bulk_store_wait_read();      // last step's row has left the tile: it may be rewritten
             if (HIST == 2 && gl == 0) {
                 const float4 f0 = lds4(EA(4)), f1 = lds4(EA(5)), f2 = lds4(EA(6)), f3 = lds4(EA(7));
                 sts4(EA(0), f0); sts4(EA(1), f1); sts4(EA(2), f2); sts4(EA(3), f3);
@@ -435,7 +444,11 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         if (live) {
             // ---- outputs: obs rows of the warp's envs are contiguous in global memory, so the tile is copied out with
             // fully coalesced 128-bit streaming stores.
+            if (SHIPSIM_TMA_STORE) fence_proxy_async();     // this lane's writes to the tiles (its own frame, other envs' rays)
             __syncwarp();
+#if SHIPSIM_TMA_STORE
+            if (p.obs && leader) bulk_store(p.obs + ((size_t)k * p.N + e) * OBS4, EA(0), OBS4 * 16);
+#else
             // lane -> (row lane / OBS4, column lane % OBS4), each further round moves 32 / OBS4 rows down.  A round is real
             // iff its row belongs to an env of this batch, i.e. iff its address lies before the end of this step's rows
             // (tested against the step's end pointer, which moves with k: a loop-invariant row limit was hoisted, spilled
@@ -448,6 +461,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 for (int i = 0; i < (EPW * OBS4 >= 32 ? EPW * OBS4 / 32 : 1); ++i)
                     if (o + i * 32 < o_end) __stcs(o + i * 32, lds4(cp_src + i * (32 / OBS4) * (EB4 * 16)));
             }
+#endif
             if (leader) {
                 const size_t row = (size_t)k * p.N + e;
                 if (p.reward) p.reward[row] = reward;
@@ -457,6 +471,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         __syncwarp();                           // copy-out done and plane rows complete before the next iteration
     }
     // the loop leaves the pose of the last step in r (no integration after it)
+    if (SHIPSIM_TMA_STORE) bulk_store_wait_read();
     if (leader) {
         const float4 l1 = lds4(EA(OBS4 - 3)), l2 = lds4(EA(OBS4 - 2)), l3 = lds4(EA(OBS4 - 1));
         r.episode = __float_as_int(lds1(EA(GOL + 2) + 12));
