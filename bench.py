@@ -561,6 +561,17 @@ def extra_configs(torch, dev, rank, world):
                                   "roofline_frac": rate * b_alg(1) / 1e9 / peak}
         env.close()
         del env
+        # configs[1] with a new map for every episode (game.py:271-272): the device-generated bank is
+        # regenerated slice by slice on a side stream, one period per 1,000-step rollout
+        env = BatchedShipEnv(ENVS, n_scenarios=N_SCENARIOS, seed=SEED, device=dev, scenario_source="device", fresh_maps=True,
+                             validate_actions=False)
+        env.reset()
+        ms = _single_rank_timed(torch, dev, env, ROLLOUT, 10)
+        rate = ENVS * ROLLOUT / (ms * 1e-3)
+        res["default_4096_fresh_maps"] = {"env_steps_per_s": rate, "launch_ms": ms, "K": ROLLOUT, "kernel": kernel_name(env.launch_info()),
+                                          "roofline_frac": rate * b_alg(ROLLOUT) / 1e9 / peak, "fresh": env.fresh_info()}
+        env.close()
+        del env
         # configs[2]: builder-defined "max difficulty" map: 1000x1000, N=30, width_frac=0.9, 180 deg fan
         class GC(GameConfig):
             BOUNDS = (1000, 1000)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SHIPSIM_ABI_VERSION 3
+#define SHIPSIM_ABI_VERSION 4
 #define SHIPSIM_N_GOALS 5        /* game.py:17  N_GOALS */
 #define SHIPSIM_N_BEAMS 10       /* models.py:29 LiDAR(n_beams=10): the only beam count the reference ever uses */
 #define SHIPSIM_FRAME 16         /* ship_env.py:43 n_states = 2+1+1+2+n_beams */
@@ -135,6 +135,16 @@ int shipsim_load_scenarios(shipsim_t *h, const double *host_hull_xy, const int32
  * the distributions are the reference's, the individual maps are not (CPython's Mersenne Twister cannot be matched).
  * Work is enqueued on `stream`; the call waits for it (a 4-byte read-back sizes the SAT pass). */
 int shipsim_generate_scenarios(shipsim_t *h, int32_t n_scenarios, uint64_t seed, int32_t map_N, float width_frac, void *stream);
+
+/* Fresh maps in the reset path (ShipGame.reset builds a new level for every episode: game.py:271-272, game_map.py:22-73).
+ * With enable != 0 the device-generated bank (shipsim_generate_scenarios; 4 * 2^k scenarios; auto_reset on) is treated as
+ * four slices: resets of period p -- a period lasts at least max_steps env-steps, so an episode ends no later than the
+ * period after the one it began in -- pick from slice p % 4, walking it with a per-env offset and odd stride (an env
+ * does not meet a map twice), while the slice two periods ahead is regenerated with a new seed on a side stream.  No
+ * map is played again once its slice has been retired.  enable == 0 returns to the fixed bank. */
+int shipsim_fresh_maps(shipsim_t *h, int32_t enable);
+/* info[8] = enabled, period, first scenario and size of the slice resets pick from, regeneration count of the 4 slices. */
+int shipsim_fresh_info(const shipsim_t *h, int32_t *info);
 
 /* Read the device-generated bank back (validation / inspection): host_hull_xy[n][2][SHIPSIM_MAX_HULL][2] (CCW, zero
  * padded), host_hull_n[n][2], host_goals[n][5][2]; hull vertices are the fp32-rounded ones the kernels use. */

@@ -48,6 +48,8 @@ typedef struct {
     int32_t auto_reset;          /* SubprocVecEnv worker semantics */
     int32_t n_scenarios;
     int32_t maxv;                /* row stride of the hull arrays (<= ORC_MAXV) */
+    int32_t pick_base;           /* fresh-maps mode of the product (pick_count > 0, a power of two): resets walk the bank slice */
+    int32_t pick_count;          /* [pick_base, pick_base + pick_count) with a per-env offset and odd stride                  */
 } orc_config;
 
 /* scenario bank, flat: hull_xy[s][b][maxv][2], hull_n[s][b], goals[s][5][2] */
@@ -102,6 +104,18 @@ int32_t orc_pick_scenario(uint64_t seed, int64_t gid, int32_t episode, int32_t n
     uint32_t r[4];
     orc_philox4x32(seed, (uint64_t)gid, (uint32_t)episode, ORC_STREAM_SCENARIO, r);
     return (int32_t)(((uint64_t)r[0] * (uint64_t)n_scenarios) >> 32);
+}
+
+/* the reference builds a new level per reset (game.py:271-272); which stored scenario stands in for it is the product's
+ * bookkeeping, restated here so that auto-reset trajectories can be compared */
+static int32_t pick_for(const orc_config *c, int64_t gid, int32_t episode)
+{
+    if (c->pick_count > 0) {
+        uint32_t r[4];
+        orc_philox4x32(c->seed, (uint64_t)gid, 0xffffffffu, ORC_STREAM_SCENARIO, r);
+        return c->pick_base + (int32_t)((r[0] + (uint32_t)episode * (r[1] | 1u)) & (uint32_t)(c->pick_count - 1));
+    }
+    return orc_pick_scenario(c->seed, gid, episode, c->n_scenarios);
 }
 
 int32_t orc_random_action(uint64_t seed, int64_t gid, uint32_t step)
@@ -647,7 +661,7 @@ static void step_env(const orc_config *c, const orc_derived *d, const orc_bank *
     }
     if (done && c->auto_reset) {
         const int episode = in[4] + 1;
-        const int ns = orc_pick_scenario(c->seed, c->env_id_offset + e, episode, c->n_scenarios);
+        const int ns = pick_for(c, c->env_id_offset + e, episode);
         reset_env(c, bank, s, e, ns, episode);
     }
     if (obs) memcpy(obs, hist, sizeof(double) * (size_t)F * c->history);
@@ -676,7 +690,7 @@ void orc_reset(const orc_config *c, const orc_bank *bank, const orc_state *s, in
     for (int e = 0; e < n; ++e) {
         if (mask && !mask[e]) continue;
         const int episode = first ? 0 : s->ints[(size_t)e * 5 + 4] + 1;
-        const int sc = scen ? scen[e] : orc_pick_scenario(c->seed, c->env_id_offset + e, episode, c->n_scenarios);
+        const int sc = scen ? scen[e] : pick_for(c, c->env_id_offset + e, episode);
         reset_env(c, bank, s, e, sc, episode);
         if (obs) memcpy(obs + (size_t)e * F * c->history, s->hist + (size_t)e * F * c->history, sizeof(double) * F * c->history);
     }

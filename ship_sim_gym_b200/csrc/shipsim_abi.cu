@@ -119,6 +119,19 @@ struct shipsim_handle {
     int dma_for_n = 0, dma_for_k = 0;
     int dma_step = 0, dma_dir = 1;           // the split climbs towards the shorter call: step size and direction
     double dma_last_t = 0.0;                 // seconds per env-step of the previous call
+    // fresh-maps mode (shipsim_fresh_maps): the device-generated bank is regenerated a quarter at a time behind the envs
+    struct {
+        bool on = false, pending = false;
+        int map_N = 0;
+        float width_frac = 0.f;
+        uint64_t seed = 0;
+        int period = 0;                      // resets of period p pick from quarter p % 4
+        long long steps = 0;                 // env-steps (per env) since the period began
+        int max_steps = 0;                   // the longest episode cap seen: a period lasts at least that many steps
+        int generation[4] = {0, 0, 0, 0};    // how many times each quarter has been regenerated
+        cudaStream_t stream = nullptr;
+        cudaEvent_t period_begin = nullptr, gen_done = nullptr;
+    } fresh;
     HostPool *pool = nullptr;
     int64_t last_h2d = 0, last_d2h = 0;      // bytes the last shipsim_step_host moved over PCIe
     int64_t launches = 0;
@@ -332,6 +345,9 @@ extern "C" int shipsim_destroy(shipsim_t *h)
     for (auto &ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->copy_done) if (ev) cudaEventDestroy(ev);
     if (h->trace0) cudaEventDestroy(h->trace0);
+    if (h->fresh.stream) cudaStreamDestroy(h->fresh.stream);
+    if (h->fresh.period_begin) cudaEventDestroy(h->fresh.period_begin);
+    if (h->fresh.gen_done) cudaEventDestroy(h->fresh.gen_done);
     if (h->h_rec) cudaFreeHost(h->h_rec);
     if (h->h_off) cudaFreeHost(h->h_off);
     if (h->h_count) cudaFreeHost(h->h_count);
@@ -444,6 +460,7 @@ extern "C" int shipsim_load_scenarios(shipsim_t *h, const double *hull_xy, const
     h->p.bank = d; h->p.edges_d = de; h->p.grid = dg; h->p.spawn_rows = dsp;
     const int old_n = h->p.n_scen;
     h->p.n_scen = n_scen; h->p.maxv = dev_maxv; h->p.scen_stride4 = stride4; h->p.hull_max = dev_maxv;
+    h->fresh.on = false; h->fresh.pending = false; h->p.pick_base = 0; h->p.pick_count = 0;     // (a host bank cannot be regenerated)
     h->launches += 2;
     if (h->p.state && n_scen < old_n) {      // live envs may hold ids of the old, larger bank
         CU(launch_clamp_scenarios(h->p.state, h->cfg.num_envs, n_scen, 0));
@@ -506,6 +523,8 @@ extern "C" int shipsim_generate_scenarios(shipsim_t *h, int32_t n_scen, uint64_t
     cudaFree(h->d_gen_xy); cudaFree(h->d_gen_goals); cudaFree(h->d_gen_n);
     h->d_bank = d; h->d_edges = de; h->d_grid = dg; h->d_spawn = dsp;
     h->d_gen_xy = dxy; h->d_gen_goals = dgo; h->d_gen_n = dn; h->gen_count = n_scen;
+    h->fresh.on = false; h->fresh.pending = false; h->fresh.map_N = map_N; h->fresh.width_frac = width_frac; h->fresh.seed = seed;
+    h->p.pick_base = 0; h->p.pick_count = 0;
     h->p.bank = d; h->p.edges_d = de; h->p.grid = dg; h->p.spawn_rows = dsp;
     const int old_n = h->p.n_scen;
     h->p.n_scen = n_scen; h->p.maxv = maxv; h->p.scen_stride4 = stride4; h->p.hull_max = hull_max;
@@ -527,6 +546,107 @@ extern "C" int shipsim_read_scenarios(shipsim_t *h, double *host_hull_xy, int32_
     CU(cudaMemcpy(host_hull_xy, h->d_gen_xy, S * 2 * kMaxHull * 2 * sizeof(double), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(host_hull_n, h->d_gen_n, S * 2 * sizeof(int), cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(host_goals, h->d_gen_goals, S * 10 * sizeof(double), cudaMemcpyDeviceToHost));
+    return SHIPSIM_OK;
+}
+
+// ---- fresh maps (ShipGame.reset builds a new level every time: game.py:271-272) -------------
+// The device-generated bank is cut into four slices.  Resets of period p (a period = at least max_steps env-steps, so
+// every episode that began in it ends before the next period does) pick from slice p % 4; slice (p + 1) % 4 -- last
+// picked from in period p - 3, drained during p - 2 -- is regenerated with a new seed on a side stream while period p
+// runs.  No map is played after the period following the one it was picked in, and none comes back.
+static uint64_t fresh_seed(uint64_t seed, int period) { return seed + 0x9E3779B97F4A7C15ull * (uint64_t)(period + 1); }
+
+static int fresh_regenerate(shipsim_t *h, int slice, uint64_t seed)
+{
+    const int q = h->gen_count / 4;
+    const int maxv = kMaxHull, stride4 = kBankHeader4 + 2 * maxv;
+    const size_t s0 = (size_t)slice * q;
+    cudaStream_t gs = h->fresh.stream;
+    double *dxy = h->d_gen_xy + s0 * 2 * kMaxHull * 2, *dgo = h->d_gen_goals + s0 * 10;
+    int *dn = h->d_gen_n + s0 * 2;
+    float4 *d = h->d_bank + s0 * stride4, *dsp = h->d_spawn + s0 * (1 + 2 * 4);
+    EdgeD *de = h->d_edges + s0 * 2 * kMaxHull;
+    uint4 *dg = h->d_grid + s0 * kGridN * kGridN;
+    CU(cudaMemsetAsync(d, 0, (size_t)q * stride4 * sizeof(float4), gs));
+    CU(cudaMemsetAsync(de, 0, (size_t)q * 2 * kMaxHull * sizeof(EdgeD), gs));
+    CU(launch_gen_scenarios(seed, q, h->cfg.bounds_w, h->cfg.bounds_h, h->fresh.map_N, h->fresh.width_frac, dxy, dn, dgo, gs));
+    CU(launch_pack_bank(dxy, dn, dgo, q, maxv, stride4, d, de, gs));
+    const double pad = -(double)h->p.gridp.x0;
+    const double cw = ((double)h->cfg.bounds_w + 2.0 * pad) / kGridN, ch = ((double)h->cfg.bounds_h + 2.0 * pad) / kGridN;
+    const double margin = 0.05 + 1e-4 * std::max((double)h->cfg.bounds_w, (double)h->cfg.bounds_h);
+    const double reach = std::max({(double)h->cfg.lidar_distance, (double)h->ship_reach, std::sqrt(cw * cw + ch * ch)}) + margin;
+    CU(launch_build_grid(dxy, dn, q, kMaxHull, (double)h->p.gridp.x0, (double)h->p.gridp.y0, cw, ch, reach, margin, dg, gs));
+    StepParams sp = h->p;
+    sp.bank = d; sp.edges_d = de; sp.grid = dg; sp.n_scen = q;
+    CU(launch_build_spawn_rows(sp, dsp, gs));
+    h->launches += 4;
+    return SHIPSIM_OK;
+}
+
+// called before every step launch: moves on to the next period when the current one has lasted long enough
+static int fresh_tick(shipsim_t *h, int K, cudaStream_t s)
+{
+    auto &f = h->fresh;
+    if (!f.on) return SHIPSIM_OK;
+    f.max_steps = std::max(f.max_steps, h->cfg.max_steps);
+    if (f.steps >= f.max_steps) {
+        f.period++;
+        f.steps = 0;
+        const int q = h->gen_count / 4, slice = f.period % 4;
+        if (f.pending) {                                 // this period's slice was regenerated while the last one ran
+            CU(cudaStreamWaitEvent(s, f.gen_done, 0));
+            f.pending = false;
+        }
+        h->p.pick_base = slice * q;
+        if (f.period + 1 >= 4) {                         // the slice after this one has been played: new maps for it
+            const int nxt = (f.period + 1) % 4;
+            CU(cudaEventRecord(f.period_begin, s));      // every launch that could still read it precedes this point
+            CU(cudaStreamWaitEvent(f.stream, f.period_begin, 0));
+            const int rc = fresh_regenerate(h, nxt, fresh_seed(f.seed, f.period + 1));
+            if (rc) return rc;
+            CU(cudaEventRecord(f.gen_done, f.stream));
+            f.generation[nxt]++;
+            f.pending = true;
+        }
+    }
+    f.steps += K;
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_fresh_maps(shipsim_t *h, int32_t enable)
+{
+    if (!h) return fail(SHIPSIM_ERR_ARG, "handle is NULL");
+    DeviceGuard g(h->device);
+    auto &f = h->fresh;
+    if (!enable) {
+        if (f.on) CU(cudaStreamSynchronize(f.stream));
+        f.on = false; f.pending = false;
+        h->p.pick_base = 0; h->p.pick_count = 0;
+        return SHIPSIM_OK;
+    }
+    if (!h->d_gen_xy || h->p.bank != h->d_bank || h->gen_count != h->p.n_scen)
+        return fail(SHIPSIM_ERR_STATE, "fresh maps need a device-generated bank: call shipsim_generate_scenarios first");
+    const int q = h->gen_count / 4;
+    if (h->gen_count % 4 != 0 || q < 1 || (q & (q - 1)) != 0)
+        return fail(SHIPSIM_ERR_ARG, "fresh maps need a bank of 4 * 2^k scenarios");
+    if (!h->cfg.auto_reset) return fail(SHIPSIM_ERR_STATE, "fresh maps need auto_reset (an env that is never reset would outlive its map)");
+    if (!f.stream) {
+        CU(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&f.period_begin, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&f.gen_done, cudaEventDisableTiming));
+    }
+    f.on = true; f.pending = false; f.period = 0; f.steps = 0; f.max_steps = h->cfg.max_steps;
+    for (int &gen : f.generation) gen = 0;
+    h->p.pick_base = 0; h->p.pick_count = q;
+    h->p.hull_max = std::max(h->p.hull_max, std::min(kMaxHull, f.map_N + 2));   // regenerated hulls: at most map_N + 2 vertices
+    return SHIPSIM_OK;
+}
+
+extern "C" int shipsim_fresh_info(const shipsim_t *h, int32_t *info)
+{
+    if (!h || !info) return fail(SHIPSIM_ERR_ARG, "NULL argument");
+    info[0] = h->fresh.on ? 1 : 0; info[1] = h->fresh.period; info[2] = h->p.pick_base; info[3] = h->p.pick_count;
+    for (int i = 0; i < 4; ++i) info[4 + i] = h->fresh.generation[i];
     return SHIPSIM_OK;
 }
 
@@ -581,6 +701,10 @@ static int step_impl(shipsim_t *h, const void *dev_actions, int action_dtype, in
     if (action_dtype != SHIPSIM_ACTION_RANDOM && !dev_actions) return fail(SHIPSIM_ERR_ARG, "dev_actions is NULL");
     if ((uintptr_t)dev_obs & 15) return fail(SHIPSIM_ERR_ARG, "dev_obs must be 16-byte aligned");
     DeviceGuard g(h->device);
+    {
+        const int rcf = fresh_tick(h, K, (cudaStream_t)stream);
+        if (rcf) return rcf;
+    }
     StepParams p = h->p;
     p.actions = dev_actions; p.action_dtype = action_dtype; p.K = K;
     p.obs = (float4 *)dev_obs; p.reward = dev_reward; p.done = dev_done;

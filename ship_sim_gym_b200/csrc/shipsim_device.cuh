@@ -85,6 +85,7 @@ struct StepParams {
     int action_dtype, history, auto_reset, max_steps;
     int n_scen, maxv, scen_stride4;   // maxv = edge stride of the fp32 records
     int hull_max;                     // largest hull in the bank (SAT pass lane layout)
+    int pick_base, pick_count;        // fresh-maps mode (pick_count > 0, a power of two): resets pick from this slice of the bank
     unsigned step0;              // global step counter at launch (random-action stream)
     float W, H, dt, damping;
     float lidar_len;
@@ -121,8 +122,16 @@ __device__ __forceinline__ uint4 philox4x32_10(unsigned long long seed, unsigned
     return make_uint4(c0, c1, c2, c3);
 }
 
+// Which scenario an env's next episode plays (ShipGame.reset builds a new level every time, game.py:271-272).  Finite bank:
+// a uniform draw keyed by (seed, global env id, episode).  Fresh-maps mode (shipsim_fresh_maps): the bank is regenerated
+// slice by slice behind the envs; resets pick from the slice generated last, walking it with a per-env offset and odd
+// stride, so that an env never meets the same map twice (a slice is retired before the walk could wrap: see fresh_tick).
 __device__ __forceinline__ int pick_scenario(const StepParams &p, long long gid, int episode)
 {
+    if (p.pick_count > 0) {
+        const uint4 r = philox4x32_10(p.seed, (unsigned long long)gid, 0xffffffffu, 0u);
+        return p.pick_base + (int)((r.x + (unsigned)episode * (r.y | 1u)) & (unsigned)(p.pick_count - 1));
+    }
     const uint4 r = philox4x32_10(p.seed, (unsigned long long)gid, (unsigned)episode, 0u);
     return (int)__umulhi(r.x, (unsigned)p.n_scen);
 }

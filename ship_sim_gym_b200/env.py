@@ -86,7 +86,7 @@ class BatchedShipEnv(object):
     def __init__(self, num_envs, game_config=None, env_config=None, device=None, seed=0, n_scenarios=1024,
                  bank=None, map_N=10, map_width_frac=0.5, auto_reset=True, honour_lidar_config=False,
                  env_id_offset=0, lanes_per_env=0, validate_actions=True, scenario_source="host", steps_in_flight=0,
-                 host_threads=0):
+                 host_threads=0, fresh_maps=False):
         self.knobs = snapshot(game_config, env_config, honour_lidar_config)
         if self.knobs["lidar"]["N_BEAMS"] != _abi.N_BEAMS:
             raise NotImplementedError("N_BEAMS must be 10")
@@ -159,6 +159,9 @@ class BatchedShipEnv(object):
         self._hist = None
         self.total_steps = 0
         self._state_bound = True
+        self.graph_safe = True                 # False: kernel parameters change between launches (no CUDA-graph replay)
+        if fresh_maps:
+            self.fresh_maps(True)
 
     # ------------------------------------------------------------------------------------------ plumbing
     def _stream(self):
@@ -205,6 +208,21 @@ class BatchedShipEnv(object):
         self._n_scen = int(n_scenarios)
         self.params_epoch = getattr(self, "params_epoch", 0) + 1
         self._needs_reset = True
+
+    def fresh_maps(self, enable=True):
+        """A new map for every episode, as ShipGame.reset builds one (game.py:271-272): the device-generated bank
+        (`scenario_source="device"` or `generate_scenarios`; 4 * 2^k scenarios) is regenerated slice by slice on a side
+        stream behind the envs, and resets only pick from the newest slice (shipsim_fresh_maps).  Needs auto_reset."""
+        with torch.cuda.device(self.device):
+            _abi.check(self.L.shipsim_fresh_maps(self._h, int(bool(enable))))
+        self.graph_safe = not enable
+        self.params_epoch += 1
+
+    def fresh_info(self):
+        """dict(enabled, period, pick_base, pick_count, generation[4]) of the fresh-maps rotation."""
+        a = (C.c_int32 * 8)()
+        _abi.check(self.L.shipsim_fresh_info(self._h, a))
+        return {"enabled": bool(a[0]), "period": a[1], "pick_base": a[2], "pick_count": a[3], "generation": list(a[4:8])}
 
     def read_scenarios(self):
         """The device-generated bank as a host ScenarioBank (validation / inspection)."""

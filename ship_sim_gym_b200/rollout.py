@@ -149,7 +149,7 @@ class RolloutCollector(object):
             if self.env.last_reset_obs is not None:
                 self.obs[0].copy_(self.env.last_reset_obs)
             self._seen_reset_epoch = self.env.reset_epoch
-        if not self.use_graph:
+        if not self.use_graph or not getattr(self.env, "graph_safe", True):     # (fresh maps: the pick slice moves between launches)
             self._collect()
         else:
             if self._graph is not None and self._graph_epoch != self.env.params_epoch:

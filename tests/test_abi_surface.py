@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     lib = _abi.load()
     for name in _declared():
         assert getattr(lib, name) is not None, name
-    assert lib.shipsim_abi_version() == 3
+    assert lib.shipsim_abi_version() == 4
     # the dynamic symbol table too (what a cgo / JNI / ctypes binder would resolve against)
     out = subprocess.run(["nm", "-D", "--defined-only", _abi.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r"\bT (shipsim_[a-z_0-9]+)", out))
