@@ -40,7 +40,7 @@ typedef struct {
     double goal_radius;          /* game.py:82 (5) */
     double step_penalty;         /* ship_env.py:13 (-0.01) */
     double spawn_y;              /* game.py:274 (25) */
-    uint64_t seed;               /* scenario choice on auto-reset: philox(seed, global env id, episode) */
+    uint64_t seed;               /* scenario choice on auto-reset: hash(seed, global env id, episode) */
     int64_t env_id_offset;       /* global id of env 0 (multi-GPU sharding) */
     int32_t max_steps;           /* config.py:16 */
     int32_t history;             /* config.py:15 */
@@ -99,21 +99,35 @@ void orc_philox4x32(uint64_t seed, uint64_t ctr_lo, uint32_t ctr2, uint32_t ctr3
 #define ORC_STREAM_SCENARIO 0u
 #define ORC_STREAM_ACTION 1u
 
-int32_t orc_pick_scenario(uint64_t seed, int64_t gid, int32_t episode, int32_t n_scenarios)
+/* Scenario picks: the product's bookkeeping (the reference builds a new level per reset, game.py:271-272, and has no
+ * bank), restated so that auto-reset trajectories can be compared: an integer hash of (seed, global env id, episode). */
+static uint32_t mix32(uint32_t x)
 {
-    uint32_t r[4];
-    orc_philox4x32(seed, (uint64_t)gid, (uint32_t)episode, ORC_STREAM_SCENARIO, r);
-    return (int32_t)(((uint64_t)r[0] * (uint64_t)n_scenarios) >> 32);
+    x ^= x >> 17; x *= 0xed5ad4bbu; x ^= x >> 11; x *= 0xac4c1b51u; x ^= x >> 15; x *= 0x31848babu; x ^= x >> 14;
+    return x;
 }
 
-/* the reference builds a new level per reset (game.py:271-272); which stored scenario stands in for it is the product's
- * bookkeeping, restated here so that auto-reset trajectories can be compared */
+static uint32_t pick_key(uint64_t seed, int64_t gid)
+{
+    uint32_t k = mix32((uint32_t)seed ^ 0x9E3779B9u);
+    k = mix32(k ^ (uint32_t)(seed >> 32));
+    k = mix32(k ^ (uint32_t)(uint64_t)gid);
+    return mix32(k ^ (uint32_t)((uint64_t)gid >> 32));
+}
+
+int32_t orc_pick_scenario(uint64_t seed, int64_t gid, int32_t episode, int32_t n_scenarios)
+{
+    const uint32_t h = mix32(pick_key(seed, gid) + (uint32_t)episode * 0x9E3779B9u);
+    return (int32_t)(((uint64_t)h * (uint64_t)n_scenarios) >> 32);
+}
+
+/* fresh-maps mode: a walk through the newest slice of the bank with a per-env offset and odd stride */
 static int32_t pick_for(const orc_config *c, int64_t gid, int32_t episode)
 {
     if (c->pick_count > 0) {
-        uint32_t r[4];
-        orc_philox4x32(c->seed, (uint64_t)gid, 0xffffffffu, ORC_STREAM_SCENARIO, r);
-        return c->pick_base + (int32_t)((r[0] + (uint32_t)episode * (r[1] | 1u)) & (uint32_t)(c->pick_count - 1));
+        const uint32_t key = pick_key(c->seed, gid);
+        const uint32_t stride = mix32(key ^ 0x5bd1e995u) | 1u;
+        return c->pick_base + (int32_t)((key + (uint32_t)episode * stride) & (uint32_t)(c->pick_count - 1));
     }
     return orc_pick_scenario(c->seed, gid, episode, c->n_scenarios);
 }

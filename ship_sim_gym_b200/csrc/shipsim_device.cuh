@@ -123,17 +123,36 @@ __device__ __forceinline__ uint4 philox4x32_10(unsigned long long seed, unsigned
 }
 
 // Which scenario an env's next episode plays (ShipGame.reset builds a new level every time, game.py:271-272).  Finite bank:
-// a uniform draw keyed by (seed, global env id, episode).  Fresh-maps mode (shipsim_fresh_maps): the bank is regenerated
-// slice by slice behind the envs; resets pick from the slice generated last, walking it with a per-env offset and odd
-// stride, so that an env never meets the same map twice (a slice is retired before the walk could wrap: see fresh_tick).
-__device__ __forceinline__ int pick_scenario(const StepParams &p, long long gid, int episode)
+// a uniform draw keyed by (seed, global env id, episode) -- an integer hash (three multiply-xorshift rounds per word, the
+// "triple32" finaliser), not Philox: a pick sits on the reset path of both kernels, where the ten Philox rounds were 6 %
+// of the window kernel's instructions (profiles/r02_*), and nothing but uniformity and independence of the sharding
+// is asked of it.  Fresh-maps mode (shipsim_fresh_maps): the bank is regenerated slice by slice behind the envs; resets
+// pick from the slice generated last, walking it with a per-env offset and odd stride, so that an env never meets the
+// same map twice (a slice is retired before the walk could wrap: see fresh_tick).
+__device__ __forceinline__ unsigned mix32(unsigned x)
+{
+    x ^= x >> 17; x *= 0xed5ad4bbu; x ^= x >> 11; x *= 0xac4c1b51u; x ^= x >> 15; x *= 0x31848babu; x ^= x >> 14;
+    return x;
+}
+// everything of a pick but the episode number (constant per env)
+__device__ __forceinline__ unsigned pick_key(const StepParams &p, long long gid)
+{
+    unsigned k = mix32((unsigned)p.seed ^ 0x9E3779B9u);
+    k = mix32(k ^ (unsigned)(p.seed >> 32));
+    k = mix32(k ^ (unsigned)(unsigned long long)gid);
+    return mix32(k ^ (unsigned)((unsigned long long)gid >> 32));
+}
+__device__ __forceinline__ int pick_scenario_keyed(const StepParams &p, unsigned key, int episode)
 {
     if (p.pick_count > 0) {
-        const uint4 r = philox4x32_10(p.seed, (unsigned long long)gid, 0xffffffffu, 0u);
-        return p.pick_base + (int)((r.x + (unsigned)episode * (r.y | 1u)) & (unsigned)(p.pick_count - 1));
+        const unsigned stride = mix32(key ^ 0x5bd1e995u) | 1u;
+        return p.pick_base + (int)((key + (unsigned)episode * stride) & (unsigned)(p.pick_count - 1));
     }
-    const uint4 r = philox4x32_10(p.seed, (unsigned long long)gid, (unsigned)episode, 0u);
-    return (int)__umulhi(r.x, (unsigned)p.n_scen);
+    return (int)__umulhi(mix32(key + (unsigned)episode * 0x9E3779B9u), (unsigned)p.n_scen);
+}
+__device__ __forceinline__ int pick_scenario(const StepParams &p, long long gid, int episode)
+{
+    return pick_scenario_keyed(p, pick_key(p, gid), episode);
 }
 
 __device__ __forceinline__ int random_action(const StepParams &p, long long gid, unsigned step)

@@ -132,7 +132,8 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
     // that at a reset the Philox rounds are not in front of the loads of the new scenario's goals and spawn row, and
     // every window pulls those few lines towards L1 in case it ends in a reset.
     constexpr int SPL = (kScr4 + T - 1) / T;    // spawn-row float4s per lane
-    int next_scen = pick_scenario(p, gid, r.episode + 1);
+    const unsigned pkey = pick_key(p, gid);
+    int next_scen = pick_scenario_keyed(p, pkey, r.episode + 1);
     int a_my = 3, a_nx = 3;
     if (valid && t < p.K) a_my = load_action(p, act0 + (size_t)t * act_stride, t, gid);
     if (valid && T + t < p.K) a_nx = load_action(p, act0 + (size_t)(T + t) * act_stride, T + t, gid);
@@ -516,7 +517,7 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
             const float4 rg0 = __ldg(rec + 2), rg1 = __ldg(rec + 3), rg2 = __ldg(rec + 4);
 #pragma unroll
             for (int i = 0; i < SPL; ++i) if (t + i * T < kScr4) spv[i] = __ldg(sp + t + i * T);
-            next_scen = pick_scenario(p, gid, ep + 1);
+            next_scen = pick_scenario_keyed(p, pkey, ep + 1);
             float2 gn[kGoals];
             unpack_goals(rg0, rg1, rg2, gn);
             float rgx, rgy;

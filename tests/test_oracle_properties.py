@@ -179,3 +179,25 @@ def test_point_distance_matches_edgewise_minimum():
             best = min(best, np.linalg.norm(p - (a + t * (b - a))))
         want = -best if _inside(h, p) else best                     # cpPolyShapePointQuery: negative inside
         assert cbind.poly_point_distance(h, p) == pytest.approx(want, abs=1e-9)
+
+
+def test_scenario_picks_are_uniform_and_independent_of_neighbours():
+    """The scenario an env plays next is an integer hash of (seed, global env id, episode) (the reference has no bank: it
+    builds a level per reset, game.py:271-272).  What the batched env needs of it: uniform over the bank, no correlation
+    between consecutive episodes of an env or between neighbouring envs, sensitive to every key word."""
+    n_scen, n_env, n_ep = 64, 512, 256
+    picks = np.array([[cbind.pick_scenario(12345, g, ep, n_scen) for ep in range(n_ep)] for g in range(n_env)])
+    assert picks.min() == 0 and picks.max() == n_scen - 1
+    counts = np.bincount(picks.ravel(), minlength=n_scen)
+    expect = picks.size / n_scen
+    chi2 = ((counts - expect) ** 2 / expect).sum()
+    assert chi2 < 120, chi2                     # 63 degrees of freedom: mean 63, sd 11
+    # consecutive episodes of an env, neighbouring envs at the same episode: pairs uniform over n_scen^2 -> equal with p = 1/n_scen
+    same_next = (picks[:, 1:] == picks[:, :-1]).mean()
+    same_nb = (picks[1:] == picks[:-1]).mean()
+    assert abs(same_next - 1 / n_scen) < 0.004 and abs(same_nb - 1 / n_scen) < 0.004, (same_next, same_nb)
+    # every word of the key matters: high seed word, high env-id word
+    a = np.array([cbind.pick_scenario(12345, g, 3, 1 << 20) for g in range(64)])
+    b = np.array([cbind.pick_scenario(12345 + (1 << 32), g, 3, 1 << 20) for g in range(64)])
+    c = np.array([cbind.pick_scenario(12345, g + (1 << 32), 3, 1 << 20) for g in range(64)])
+    assert (a != b).mean() > 0.95 and (a != c).mean() > 0.95
