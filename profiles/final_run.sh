@@ -13,4 +13,5 @@ python bench.py --impl reference --steps 10 --warmup 2 > $O/${S}_bench_reference
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${S}_launches.csv python bench.py --steps 2 --warmup 1 > $O/${S}_bench_under_ncu.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:window_kernel -s 5 -c 1 -f -o $O/${S}_win python profiles/prof_driver.py --envs 4096 --K 1000 --reps 3 > $O/${S}_ncu_win.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 5 -c 1 -f -o $O/${S}_step python profiles/prof_driver.py --envs 1048576 --K 32 --reps 3 --window 1 > $O/${S}_ncu_step.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 5 -c 1 -f -o $O/${S}_hard python profiles/prof_driver.py --envs 65536 --K 100 --reps 3 --window 1 --hard > $O/${S}_ncu_hard.log 2>&1
 ls -la $O | tail -12
