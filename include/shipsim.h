@@ -206,6 +206,18 @@ int shipsim_expand_delta(float *host_obs, float *host_reward, uint8_t *host_done
                          const float *host_var, float *host_cur, int32_t n_steps, int64_t num_envs, float step_penalty,
                          int32_t cut_on_done, int32_t history);
 
+/* The policy half of an on-device rollout step (BASELINE configs[4]): stable-baselines' MlpPolicy as the reference trains it
+ * (train/stable_baselines/ppo.py:88: separate tanh trunks obs -> 64 -> 64 for the policy and the value function, heads of 3
+ * logits and 1 value) for num_envs observation rows of 32 floats, and the categorical sample by Gumbel-max.  fp32, one launch.
+ * Layouts (device memory, row-major): dev_w1[32][128] = [policy | value] first layers side by side (any observation scale
+ * folded in), dev_b1[128]; dev_w2[2][64][64] = the trunks' second layers (in x out), dev_b2[128]; dev_w3[128][4] = policy head in
+ * rows 0..63 x columns 0..2, value head in rows 64..127 x column 3 (the other entries are not read), dev_b3[4];
+ * dev_noise[num_envs][3] Gumbel(0, 1) draws.  Outputs: dev_out[num_envs][4] = 3 logits | value, dev_actions[num_envs] =
+ * argmax(logits + noise) as int64 -- the dtype shipsim_step takes as SHIPSIM_ACTION_I64.  Enqueued on `stream`. */
+int shipsim_mlp_policy_forward(const float *dev_obs, int32_t num_envs, const float *dev_w1, const float *dev_b1, const float *dev_w2,
+                               const float *dev_b2, const float *dev_w3, const float *dev_b3, const float *dev_noise, float *dev_out,
+                               int64_t *dev_actions, void *stream);
+
 /* Reduce the per-CTA statistic slots into dev_out[SHIPSIM_STATS_LEN] doubles (device memory, e.g. the tensor
  * handed to ncclAllReduce); clear != 0 zeroes the slots afterwards.  Replaces the counters ShipEnv keeps on the
  * Python object (ship_env.py:150,152,177). */

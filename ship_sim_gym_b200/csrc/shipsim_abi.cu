@@ -1033,6 +1033,18 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     return SHIPSIM_OK;
 }
 
+extern "C" int shipsim_mlp_policy_forward(const float *dev_obs, int32_t num_envs, const float *dev_w1, const float *dev_b1, const float *dev_w2,
+                                          const float *dev_b2, const float *dev_w3, const float *dev_b3, const float *dev_noise, float *dev_out,
+                                          int64_t *dev_actions, void *stream)
+{
+    if (!dev_obs || !dev_w1 || !dev_b1 || !dev_w2 || !dev_b2 || !dev_w3 || !dev_b3 || !dev_noise || !dev_out || !dev_actions || num_envs < 1)
+        return fail(SHIPSIM_ERR_ARG, "NULL buffer or num_envs < 1");
+    if (((uintptr_t)dev_obs & 15) != 0) return fail(SHIPSIM_ERR_ARG, "dev_obs must be 16-byte aligned");
+    CU(launch_mlp_policy(dev_obs, num_envs, dev_w1, dev_b1, dev_w2, dev_b2, dev_w3, dev_b3, dev_noise, dev_out, (long long *)dev_actions,
+                         (cudaStream_t)stream));
+    return SHIPSIM_OK;
+}
+
 extern "C" int shipsim_host_traffic(const shipsim_t *h, int64_t *h2d_bytes, int64_t *d2h_bytes)
 {
     if (!h) return fail(SHIPSIM_ERR_ARG, "NULL argument");

@@ -38,10 +38,12 @@ class RolloutCollector(object):
     side by side (the observation scale folded into its weights), layers 2 and 3 block-diagonal -- through `addmm`
     into preallocated buffers: 3 GEMMs + 2 tanh per step instead of 6 + 4 + 1; the Gumbel noise of the whole rollout is
     drawn once; log-probabilities, values and the GAE deltas are computed for all steps at once after the loop, which
-    leaves one fused multiply-add per step for the GAE recurrence.  Per step: 7 torch kernels + the env kernel.
+    leaves one fused multiply-add per step for the GAE recurrence.  Per step: 7 torch kernels + the env kernel -- or, for
+    the reference's own shape (32 -> 64 -> 64 -> 3 | 1), ONE launch of the library's policy kernel (both trunks, heads and
+    the Gumbel-max sample: `shipsim_mlp_policy_forward`) + the env kernel.
     Any other policy module (`forward(obs) -> (logits, value)`) takes the generic per-step path."""
 
-    def __init__(self, env, policy, T=128, gamma=0.99, lam=0.95, use_graph=True):
+    def __init__(self, env, policy, T=128, gamma=0.99, lam=0.95, use_graph=True, use_kernel=True):
         assert isinstance(env, BatchedShipEnv) and env.history <= 2
         self.env, self.policy, self.T, self.gamma, self.lam = env, policy, int(T), gamma, lam
         N, D, dev = env.num_envs, env.states_history, env.device
@@ -58,13 +60,17 @@ class RolloutCollector(object):
         self._graph = None
         self._graph_epoch = -1
         self._fused = isinstance(policy, MlpPolicy)
+        self._kernel = False
         if self._fused:
             lin = [policy.pi[0], policy.pi[2], policy.pi[4], policy.vf[0], policy.vf[2], policy.vf[4]]
             H, A = lin[0].out_features, lin[2].out_features
             assert lin[0].in_features == D and lin[3].out_features == H and lin[5].out_features == 1
             self._alloc_fused(N, D, H, A, T, f32)
             self._z = torch.empty(N, A, **f32)
+            # the library's fused policy kernel (shipsim_mlp_policy_forward) has the reference's shape built in
+            self._kernel = bool(use_kernel) and (D, H, A) == (32, 64, 3)
         self._noise = torch.empty(T, N, policy.pi[4].out_features if self._fused else 3, **f32)
+        self._a_spare = torch.empty(N, dtype=torch.int64, device=dev)
         self._nonterm = torch.empty(T, N, **f32)
         self._coef = torch.empty(T, N, **f32)
         self._delta = torch.empty(T, N, **f32)
@@ -76,6 +82,7 @@ class RolloutCollector(object):
         self._H, self._A = H, A
         self._W1, self._b1 = torch.empty(D, 2 * H, **f32), torch.empty(2 * H, **f32)             # [pi | vf] side by side
         self._W2, self._b2 = torch.zeros(2 * H, 2 * H, **f32), torch.empty(2 * H, **f32)           # block-diagonal
+        self._W2p = torch.empty(2, H, H, **f32)                                                    # the two blocks, packed (policy kernel)
         self._W3, self._b3 = torch.zeros(2 * H, A + 1, **f32), torch.empty(A + 1, **f32)           # pi -> columns 0..A-1, vf -> column A
         self._h1, self._h2 = torch.empty(N, 2 * H, **f32), torch.empty(N, 2 * H, **f32)
         self._out = torch.empty(T + 1, N, A + 1, **f32)         # logits | value of every step
@@ -87,6 +94,7 @@ class RolloutCollector(object):
         self._W1.mul_(self.policy.obs_scale)
         self._b1[:H].copy_(pi[0].bias); self._b1[H:].copy_(vf[0].bias)
         self._W2[:H, :H].copy_(pi[2].weight.t()); self._W2[H:, H:].copy_(vf[2].weight.t())
+        self._W2p[0].copy_(pi[2].weight.t()); self._W2p[1].copy_(vf[2].weight.t())
         self._b2[:H].copy_(pi[2].bias); self._b2[H:].copy_(vf[2].bias)
         self._W3[:H, :A].copy_(pi[4].weight.t()); self._W3[H:, A:].copy_(vf[4].weight.t())
         self._b3[:A].copy_(pi[4].bias); self._b3[A:].copy_(vf[4].bias)
@@ -98,6 +106,18 @@ class RolloutCollector(object):
         torch.addmm(self._b2, self._h1, self._W2, out=self._h2).tanh_()
         torch.addmm(self._b3, self._h2, self._W3, out=self._out[t])
 
+    def _forward_kernel(self, t):
+        """Both trunks, the heads and the Gumbel-max sample of step t in ONE launch of the library's policy kernel
+        (csrc/shipsim_policy.cu): logits | value -> _out[t], action -> actions[t] (t = T: values only, sample discarded)."""
+        from . import _abi
+        env = self.env
+        act = self.actions[t] if t < self.T else self._a_spare
+        nz = self._noise[t] if t < self.T else self._noise[0]
+        with torch.cuda.device(env.device):
+            _abi.check(env.L.shipsim_mlp_policy_forward(self.obs[t].data_ptr(), env.num_envs, self._W1.data_ptr(), self._b1.data_ptr(),
+                                                        self._W2p.data_ptr(), self._b2.data_ptr(), self._W3.data_ptr(), self._b3.data_ptr(),
+                                                        nz.data_ptr(), self._out[t].data_ptr(), act.data_ptr(), env._stream()))
+
     @torch.no_grad()
     def _collect(self):
         env, T = self.env, self.T
@@ -107,11 +127,17 @@ class RolloutCollector(object):
             A = self._A
             self._refresh_fused()
             for t in range(T):
-                self._forward_fused(t)
-                torch.add(self._out[t, :, :A], self._noise[t], out=self._z)
-                torch.argmax(self._z, dim=-1, out=self.actions[t])
+                if self._kernel:                            # 2 launches per step: policy + sample, env step
+                    self._forward_kernel(t)
+                else:
+                    self._forward_fused(t)
+                    torch.add(self._out[t, :, :A], self._noise[t], out=self._z)
+                    torch.argmax(self._z, dim=-1, out=self.actions[t])
                 env.rollout(self.actions[t:t + 1], out=(self.obs[t + 1:t + 2], self.rewards[t:t + 1], self.dones[t:t + 1]))
-            self._forward_fused(T)
+            if self._kernel:
+                self._forward_kernel(T)
+            else:
+                self._forward_fused(T)
             self.values.copy_(self._out[:, :, A])
             self.logp.copy_(torch.log_softmax(self._out[:T, :, :A], dim=-1).gather(-1, self.actions[:, :, None]).squeeze(-1))
         else:

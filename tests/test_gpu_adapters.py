@@ -128,6 +128,49 @@ def test_policy_rollout_graph_replay_matches_eager():
         assert ((first == -1).all(-1) == d).all()                 # the older frame is all -1 exactly on reset steps
 
 
+@pytest.mark.parametrize("n", [16384, 1000, 7])
+def test_policy_kernel_matches_the_torch_module(n):
+    """shipsim_mlp_policy_forward (csrc/shipsim_policy.cu: both MlpPolicy trunks, heads and the Gumbel-max sample in one
+    launch; train/stable_baselines/ppo.py:88) against the plain fp32 torch module: logits and values within 2e-5, the same
+    action wherever the decision is not a near-tie, ragged batch sizes included."""
+    from ship_sim_gym_b200 import BatchedShipEnv
+    from ship_sim_gym_b200.rollout import MlpPolicy, RolloutCollector
+    torch.manual_seed(n)
+    policy = MlpPolicy().cuda()
+    for lin in (policy.pi[4], policy.vf[4]):                      # livelier heads than the default init
+        lin.weight.data.mul_(4.0)
+    env = BatchedShipEnv(n, bank=_bank(8), seed=1)
+    col = RolloutCollector(env, policy, T=2, use_graph=False)
+    assert col._kernel
+    obs = torch.rand(n, 32, device="cuda") * 600.0
+    obs[: n // 4, :16] = -1.0                                     # reset rows look like this
+    col.obs[0].copy_(obs)
+    col._noise.uniform_().clamp_(1e-10, 1.0).log_().neg_().log_().neg_()
+    with torch.no_grad():
+        col._refresh_fused()
+        col._forward_kernel(0)
+        torch.cuda.synchronize()
+        logits, v = policy(obs)
+    got = col._out[0]
+    assert torch.allclose(got[:, :3], logits, atol=2e-5, rtol=1e-5) and torch.allclose(got[:, 3], v, atol=2e-5, rtol=1e-5)
+    z = logits + col._noise[0]
+    top2 = z.topk(2, dim=-1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-3
+    assert clear.float().mean() > 0.95
+    assert (col.actions[0][clear] == z.argmax(-1)[clear]).all()
+    assert col.actions[0].min() >= 0 and col.actions[0].max() <= 2 and len(torch.unique(col.actions[0])) == (3 if n > 100 else len(torch.unique(col.actions[0])))
+    # the collector with the kernel: same invariants as the torch path, 2 launches of ours per step
+    col.collect()
+    torch.cuda.synchronize()
+    assert torch.isfinite(col.adv).all() and (col.logp <= 0).all() and col.actions.min() >= 0 and col.actions.max() <= 2
+    with torch.no_grad():
+        lg, vv = policy(col.obs[1])
+    assert torch.allclose(col.values[1], vv, atol=2e-5, rtol=1e-5)
+    lp = torch.log_softmax(lg, -1).gather(-1, col.actions[1][:, None]).squeeze(-1)
+    assert torch.allclose(col.logp[1], lp, atol=1e-4)
+    env.close()
+
+
 def test_curriculum_driver_on_a_live_batch():
     """EnvConfig.MAX_STEPS as a curriculum knob: the cap changes on the live handle (shipsim_set_max_steps) and the
     time-out statistics follow it."""
