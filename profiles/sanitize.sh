@@ -18,3 +18,10 @@ for tool in memcheck racecheck synccheck; do
   run step_g8 $tool --envs 300 --K 48 --reps 1 --presteps 50 --window 1 --lanes 8
   run step_g1_hard $tool --envs 500 --K 32 --reps 1 --presteps 50 --window 1 --lanes 1 --hard
 done
+# round 2: the host-path kernels (compact_frames_kernel, history_rows_kernel), the fresh-maps regeneration and the policy
+# kernel, through their own GPU tests
+for tool in memcheck racecheck; do
+  timeout 1200 $CS --tool $tool --print-limit 20 python -m pytest tests/test_gpu_parity.py tests/test_gpu_scengen.py tests/test_gpu_adapters.py -x -q \
+      -k "two_engine_split or fresh_maps or policy_kernel" > $O/${S}_sanitize_round2_${tool}.log 2>&1
+  echo "round-2 kernels $tool: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $O/${S}_sanitize_round2_${tool}.log | tail -1) | $(grep -E 'passed|failed' $O/${S}_sanitize_round2_${tool}.log | tail -1)"
+done
