@@ -138,7 +138,10 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
     float c, s, hx, hy;
     sincos_fast(r.th, s, c);
     hull_half_extents(p, c, s, hx, hy);
-    fetch_cell_async(p, r.scen, r.x + hx, r.y + hy, EA(CEL));
+    // (G > 1: the lanes of a group share the env's block.  One lane fetches / writes, and wherever another lane's read and
+    // the leader's write of the same word are not already separated by a warp synchronisation, one is placed -- all of them
+    // compile away for G = 1.  compute-sanitizer racecheck: profiles/r02_x_sanitize.txt)
+    if (G == 1 || gl == 0) fetch_cell_async(p, r.scen, r.x + hx, r.y + hy, EA(CEL));
     __syncwarp();                                // ray table, statistics and tile initialisation (all per warp) are in place
 
     // Iteration k >= 0 is env-step k and starts with the pose ALREADY integrated (cpBodyUpdatePosition of step k);
@@ -212,6 +215,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             float dvx = 0.f, dvy = 0.f, dw = 0.f;
             const unsigned rud_slot = EA(OBS4 - 4) + 8;
             const float rud = lds1(rud_slot);
+            if (G > 1) __syncwarp();            // every lane has the old angle before the leader stores the new one
             if (a == 0) {                       // thrust along the heading the step starts from
                 dvx = -p.acc_dt * h0.y; dvy = p.acc_dt * h0.x; dw = -p.ang_dt * rud;
             }
@@ -230,6 +234,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
         // candidate planes, whose raw records are now copied global -> shared the same way -- with G = 1 into the plane
         // row itself, which the ray pass has finished with, otherwise into the env's own staging area
         cp_async_wait_all();
+        if (G > 1) __syncwarp();                // the leader's copy has landed before the group's other lanes look
         const uint4 cell = lds4u(EA(CEL));
         const bool near_any = leader && (cell.x | cell.y | (cell.z & 3u)) != 0u;
         const bool staged = near_any && ((cell.z >> 8) & 0xffu) <= (unsigned)kMaxCand;
@@ -258,6 +263,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
                 g[0] = make_float2(ga.x, ga.y); g[1] = make_float2(ga.z, ga.w); g[2] = make_float2(gb.x, gb.y);
                 g[3] = make_float2(gb.z, gb.w); g[4] = gc;
             }
+            if (G > 1) __syncwarp();            // every lane has the goals before the leader retires one
             unsigned cand = 0u;
 #pragma unroll
             for (int i = 0; i < kGoals; ++i) {
@@ -386,8 +392,13 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
 
             warp_stats(wb + STA * 16, lane, leader, goal_reached, done, colliding, oob, timeout, all_goals, r.ret, r.steps);
             do_reset = done && p.auto_reset;
+            int ep_g = 0;
+            if (G > 1) {                        // read by every lane while the warp is converged, before the leader stores the next one
+                ep_g = __float_as_int(lds1(EA(GOL + 2) + 12)) + 1;
+                __syncwarp();
+            }
             if (do_reset) {
-                const int ep = __float_as_int(lds1(EA(GOL + 2) + 12)) + 1;    // (only a reset needs the episode number: kept in shared memory)
+                const int ep = G > 1 ? ep_g : __float_as_int(lds1(EA(GOL + 2) + 12)) + 1;    // (only a reset needs the episode number: kept in shared memory)
                 reset_env(p, r, pick_scenario(p, p.env_id_offset + e, ep), ep);
                 c = 1.f; s = 0.f;
                 hx = 0.5f * (p.ship_aabb[2] - p.ship_aabb[0]); hy = 0.5f * (p.ship_aabb[3] - p.ship_aabb[1]);
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(THREADS, MINB) step_kernel(const __grid_consta
             r.th += r.w * p.dt;
             sincos_fast(r.th, s, c);
             hull_half_extents(p, c, s, hx, hy);
-            fetch_cell_async(p, r.scen, r.x + hx, r.y + hy, EA(CEL));
+            if (G == 1 || gl == 0) fetch_cell_async(p, r.scen, r.x + hx, r.y + hy, EA(CEL));
         }
         if (live) {
             // ---- outputs: obs rows of the warp's envs are contiguous in global memory, so the tile is copied out with
