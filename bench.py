@@ -561,6 +561,23 @@ def extra_configs(torch, dev, rank, world):
                                   "roofline_frac": rate * b_alg(1) / 1e9 / peak}
         env.close()
         del env
+        # configs[0] as the reference's own caller sees it: ONE env behind the gym facade (train/random.py:4-27), host in / host out
+        from ship_sim_gym_b200 import ShipEnv
+        fenv = ShipEnv()
+        fenv.reset()
+        import numpy as _np
+        acts = _np.random.RandomState(SEED).randint(0, 3, 2200)
+        t0 = None
+        for i, a in enumerate(acts):
+            if i == 200:
+                t0 = time.perf_counter()
+            if fenv.step(int(a))[2]:
+                fenv.reset()
+        dt = time.perf_counter() - t0
+        res["gym_facade_1_env"] = {"env_steps_per_s": 2000 / dt, "us_per_step": dt / 2000 * 1e6,
+                                   "api": "ShipEnv.step(a) -> numpy obs, float reward, bool done (shipsim_step_host, K = 1)"}
+        fenv.close()
+        del fenv
         # configs[1] with a new map for every episode (game.py:271-272): the device-generated bank is
         # regenerated slice by slice on a side stream, one period per 1,000-step rollout
         env = BatchedShipEnv(ENVS, n_scenarios=N_SCENARIOS, seed=SEED, device=dev, scenario_source="device", fresh_maps=True,

@@ -40,6 +40,11 @@ class ShipVecEnv(object):
     def step_async(self, actions):
         if self._pending is not None:
             raise RuntimeError("step_async called twice without step_wait")
+        if not self.as_tensors and not torch.is_tensor(actions) and self.batch.history <= 2:
+            # a numpy caller: one call into the C ABI's host-buffer path (no torch ops; the work is done here)
+            obs, rew, done = self.batch.step_np(np.asarray(actions))
+            self._pending = (obs.copy(), rew.copy(), done.copy(), None)
+            return
         a = torch.as_tensor(np.asarray(actions) if not torch.is_tensor(actions) else actions)
         self._pending = self.batch.step(a)       # enqueued on the GPU; nothing is waited for here
 
@@ -48,6 +53,8 @@ class ShipVecEnv(object):
             raise RuntimeError("step_wait called before step_async")
         obs, rew, done, _ = self._pending
         self._pending = None
+        if isinstance(obs, np.ndarray):
+            return obs, rew, done, self._infos
         return self._out(obs), self._out(rew), self._out(done), self._infos
 
     def step(self, actions):
@@ -93,9 +100,8 @@ class ShipVectorEnv(object):
         return obs[int(index)].cpu().numpy()
 
     def vector_step(self, actions):
-        a = torch.as_tensor(np.asarray(actions, dtype=np.int64))
-        obs, rew, done, _ = self.batch.step(a)
-        obs, rew, done = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        obs, rew, done = self.batch.step_np(np.asarray(actions, dtype=np.int64))
+        obs = obs.copy()
         n = self.num_envs
         return [obs[i] for i in range(n)], [float(rew[i]) for i in range(n)], [bool(done[i]) for i in range(n)], [{} for _ in range(n)]
 

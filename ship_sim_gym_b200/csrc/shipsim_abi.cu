@@ -741,7 +741,10 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     //  * envs [nd, N): a kernel turns the frames into 16-byte records + a stream of changed values (~20 bytes per
     //    env-step instead of 64 + 5) and host threads rebuild the rows -- reset observations included;
     // chunk by chunk, while later chunks are still being computed.  nd follows the measured balance of the two.
-    const bool frames_only = h->cfg.history == 2 && host_obs != nullptr;
+    // (Small calls -- a gym-style caller stepping a handful of envs one step at a time -- are latency bound: for them the
+    // kernel writes complete rows and everything, copies included, goes through the caller's stream with one wait.)
+    const bool small = n < ((size_t)1 << 16);
+    const bool frames_only = h->cfg.history == 2 && host_obs != nullptr && !small;
     int nd = 0;                                                      // envs [0, nd) by DMA (frames_only)
     bool adaptive = false;
     if (K > h->stage_K) {
@@ -764,7 +767,7 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
         CU(cudaEventCreateWithFlags(&h->act_up, cudaEventDisableTiming));
         if (std::getenv("SHIPSIM_HOST_TRACE")) for (auto &ev : h->trace_mid) CU(cudaEventCreate(&ev));
     }
-    int n_chunks = K >= 64 ? 16 : (K >= 8 ? 8 : 1);
+    int n_chunks = small ? 1 : (K >= 64 ? 16 : (K >= 8 ? 8 : 1));
     if (const char *ev = std::getenv("SHIPSIM_HOST_CHUNKS")) n_chunks = std::max(1, std::min({atoi(ev), (int)shipsim_handle::kMaxChunks, (int)K}));
     int kbeg[shipsim_handle::kMaxChunks + 1];
     for (int c = 0; c <= n_chunks; ++c) kbeg[c] = (int)((int64_t)K * c / n_chunks);
@@ -944,8 +947,12 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
                 }
                 prev_frames = (const float4 *)d_chunk + ((size_t)(kc - 1) * N) * 4;
             }
-            CU(cudaEventRecord(h->chunk_done[c], s));
-            CU(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+            cudaStream_t cs = h->copy_stream;
+            if (small) cs = s;                                      // one stream, no event hops
+            else {
+                CU(cudaEventRecord(h->chunk_done[c], s));
+                CU(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+            }
             if (frames_only) {
                 if (nd < (int)N) {
                     if (c == 0) {
@@ -982,13 +989,12 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
                 h->last_d2h += (int64_t)kc * N * ((host_reward ? 4 : 0) + (host_done ? 1 : 0));
                 if (host_obs) {
                     h->last_d2h += (int64_t)kc * N * row_full * sizeof(float);
-                    CU(cudaMemcpyAsync(host_obs + off * row_full, d_chunk, (size_t)kc * N * row_full * sizeof(float), cudaMemcpyDeviceToHost,
-                                       h->copy_stream));
+                    CU(cudaMemcpyAsync(host_obs + off * row_full, d_chunk, (size_t)kc * N * row_full * sizeof(float), cudaMemcpyDeviceToHost, cs));
                 }
-                if (host_reward) CU(cudaMemcpyAsync(host_reward + off, h->d_rew + off, (size_t)kc * N * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-                if (host_done) CU(cudaMemcpyAsync(host_done + off, h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, h->copy_stream));
+                if (host_reward) CU(cudaMemcpyAsync(host_reward + off, h->d_rew + off, (size_t)kc * N * sizeof(float), cudaMemcpyDeviceToHost, cs));
+                if (host_done) CU(cudaMemcpyAsync(host_done + off, h->d_done + off, (size_t)kc * N, cudaMemcpyDeviceToHost, cs));
             }
-            CU(cudaEventRecord(h->copy_done[c], h->copy_stream));
+            if (!small) CU(cudaEventRecord(h->copy_done[c], h->copy_stream));
         }
         return SHIPSIM_OK;
     }();
@@ -1004,9 +1010,9 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
         for (int c = 0; c < n_chunks; ++c) dens = std::max(dens, (double)h->h_count[c] / ((double)(kbeg[c + 1] - kbeg[c]) * (double)(N - nd)));
         h->var_density = std::max(0.9 * h->var_density, std::min(12.0, 1.25 * dens + 0.25));       // follows the need up at once, down slowly
     }
-    CU(cudaStreamSynchronize(h->copy_stream));
+    if (!small) CU(cudaStreamSynchronize(h->copy_stream));
     CU(cudaStreamSynchronize(s));
-    if (trace) {
+    if (trace && !small) {
         std::fprintf(stderr, "step_host trace (ms since the call's first stream op): host done %.2f\n",
                      std::chrono::duration<double, std::milli>(clk::now() - t_begin).count());
         for (int c = 0; c < n_chunks; ++c) {

@@ -382,6 +382,28 @@ class BatchedShipEnv(object):
         self.total_steps += K * self.num_envs
         return obs, rew, done
 
+    def step_np(self, actions):
+        """One env-step for a caller on the CPU (the gym facade, the vector-env adapters): numpy int actions [N] in,
+        (obs [N, 16 * history] float32, reward [N] float32, done [N] bool) out -- ONE call into shipsim_step_host with
+        page-locked buffers kept on the env; no torch ops, one stream wait.  The returned arrays are the env's buffers:
+        valid until the next call (copy them to keep them)."""
+        if self.history > 2:
+            obs, rew, done, _ = self.step(torch.as_tensor(np.asarray(actions)))
+            return obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy()
+        if getattr(self, "_np_bufs", None) is None:
+            pin = lambda *shape, dtype: torch.empty(*shape, dtype=dtype).pin_memory()      # noqa: E731
+            self._np_keep = (pin(1, self.num_envs, dtype=torch.int32), pin(1, self.num_envs, self._obs_dim_kernel, dtype=torch.float32),
+                             pin(1, self.num_envs, dtype=torch.float32), pin(1, self.num_envs, dtype=torch.uint8))
+            self._np_bufs = tuple(t.numpy() for t in self._np_keep)
+        a, obs, rew, done = self._np_bufs
+        a[0, :] = actions
+        if self.validate_actions:
+            assert ((a >= 0) & (a <= 2)).all(), "%r invalid" % (actions,)
+        with torch.cuda.device(self.device):
+            _abi.check(self.L.shipsim_step_host(self._h, a.ctypes.data, 1, obs.ctypes.data, rew.ctypes.data, done.ctypes.data, self._stream()))
+        self.total_steps += self.num_envs
+        return obs[0], rew[0], done[0].view(np.bool_)
+
     def host_threads(self):
         """Host threads step_host() uses to rebuild observation rows (0 before its first call)."""
         n = C.c_int32()
@@ -484,12 +506,12 @@ class ShipEnv(object):
 
     def step(self, action):
         assert self.action_space.contains(action), "%r (%s) invalid" % (action, type(action))   # ship_env.py:143
-        obs, rew, done, info = self.batch.step(torch.tensor([int(action)], dtype=torch.int32))
+        obs, rew, done = self.batch.step_np(int(action))
         self.last_action = action
         self.reward = float(rew[0])
         self.cumulative_reward += self.reward
         self.step_count += 1
-        return obs[0].cpu().numpy(), self.reward, bool(done[0]), {}
+        return obs[0].copy(), self.reward, bool(done[0]), {}
 
     def render(self, mode="human", close=False):
         if mode == "rgb_array":
