@@ -332,8 +332,8 @@ class BatchedShipEnv(object):
     def rollout(self, actions=None, K=None, out=None):
         """K consecutive env-steps in one kernel launch.  actions: int tensor [K,N] on device, or None for the
         in-kernel random agent (train/random.py:18).  `out` = (obs, reward, done) preallocated tensors."""
-        if self.history > 2:
-            raise NotImplementedError("rollout() supports HISTORY_SIZE <= 2; use step() for longer histories")
+        if self.history > 2 and out is not None:
+            raise NotImplementedError("rollout(out=...) supports HISTORY_SIZE <= 2 (longer rows are assembled from frames here)")
         if actions is not None:
             a = actions
             if a.device != self.device:
@@ -345,7 +345,27 @@ class BatchedShipEnv(object):
         else:
             assert K is not None
             a = None
+        if self.history > 2:
+            frames, rew, done = self._launch(a, K, None)          # the kernel runs in its one-frame mode
+            return self._long_history_rows(frames, done), rew, done
         return self._launch(a, K, out)
+
+    def _long_history_rows(self, frames, done):
+        """HISTORY_SIZE > 2: rows [frame t-H+1 | ... | frame t] put together from the K frames of a
+        rollout and the running history, with -1 for everything older than an env's latest reset (under auto-reset the
+        frame of a done step IS the reset frame: ship_env.py:180-184)."""
+        K, N, H, F = frames.shape[0], self.num_envs, self.history, _abi.FRAME
+        prev = self._hist.view(N, H, F).permute(1, 0, 2)          # [H][N][F], oldest first
+        allf = torch.cat([prev, frames], dim=0)                   # frame of step k sits at index H + k
+        rows = allf.unfold(0, H, 1)[1:].permute(0, 1, 3, 2)       # [K][N][H][F]: rows[k] = frames k-H+1 .. k
+        if self.auto_reset:
+            k_idx = torch.arange(K, device=self.device)[:, None]
+            last_reset = torch.where(done.bool(), k_idx, torch.full_like(k_idx, -(1 << 30))).cummax(dim=0).values      # [K][N]
+            slot_time = k_idx[:, :, None] - torch.arange(H - 1, -1, -1, device=self.device)[None, None, :]             # [K][1][H]
+            rows = torch.where((slot_time < last_reset[:, :, None])[..., None], torch.full_like(rows, -1.0), rows)
+        rows = rows.reshape(K, N, H * F).contiguous()
+        self._hist = rows[-1].clone()
+        return rows
 
     def alloc_rollout(self, K):
         N = self.num_envs
@@ -367,8 +387,15 @@ class BatchedShipEnv(object):
     def step_host(self, actions, K=1, out=None):
         """The CPU-caller path: numpy/pinned int32 actions [K,N] in, numpy obs/reward/done out, with the
         host<->device copies inside (shipsim_step_host)."""
-        if self.history > 2:
-            raise NotImplementedError
+        if self.history > 2:          # (rows assembled on the device, then copied: this path is not tuned for long histories)
+            o, r, d = self.rollout(torch.as_tensor(np.ascontiguousarray(actions, dtype=np.int32).reshape(K, self.num_envs)))
+            res = (o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy())
+            if out is not None:
+                for dst, src in zip(out, res):
+                    if dst is not None:
+                        dst[...] = src
+                return out
+            return res
         a = np.ascontiguousarray(actions, dtype=np.int32).reshape(K, self.num_envs)
         if self.validate_actions:
             assert ((a >= 0) & (a <= 2)).all(), "%r invalid" % (actions,)

@@ -360,3 +360,38 @@ def test_host_path_two_engine_split(dma_envs, monkeypatch):
         assert len(seen) > 1          # the split moved between calls (it follows the measured balance)
     for e in envs:
         e.close()
+
+
+@pytest.mark.parametrize("auto_reset", [True, False])
+def test_long_history_rollout_matches_single_steps(auto_reset):
+    """HISTORY_SIZE > 2 (config.py:15; SURVEY App. A note N2): rollout() assembles the rows [frame t-H+1 | ... | frame t]
+    from the frames of a K-step launch and the running history, -1 behind an env's latest reset (ship_env.py:180-184).
+    Same rows, bit for bit, as K calls of step(), across consecutive rollouts, and through step_host."""
+    from ship_sim_gym_b200 import BatchedShipEnv, ScenarioBank
+    from ship_sim_gym_b200.config import EnvConfig, GameConfig
+
+    class EC(EnvConfig):
+        HISTORY_SIZE = 4
+        MAX_STEPS = 25
+    n, K = 300, 40
+    bank = ScenarioBank.generate(16, (600, 600), seed=2)
+    envs = [BatchedShipEnv(n, GameConfig, EC, bank=bank, seed=1, auto_reset=auto_reset) for _ in range(2)]
+    rng = np.random.RandomState(7)
+    o0 = [e.reset() for e in envs]
+    assert o0[0].shape == (n, 64) and torch.equal(o0[0], o0[1])
+    for it in range(3):
+        acts = torch.tensor(rng.randint(0, 3, (K, n)).astype(np.int32), device="cuda")
+        if it < 2:
+            ro, rr, rd = envs[0].rollout(acts)
+        else:
+            ho, hr, hd = envs[0].step_host(acts.cpu().numpy(), K=K)
+            ro, rr, rd = torch.tensor(ho, device="cuda"), torch.tensor(hr, device="cuda"), torch.tensor(hd, device="cuda")
+        assert ro.shape == (K, n, 64)
+        for k in range(K):
+            so, sr, sd, _ = envs[1].step(acts[k])
+            assert torch.equal(ro[k], so), (it, k)
+            assert torch.equal(rr[k], sr) and torch.equal(rd[k].bool(), sd)
+    if auto_reset:
+        assert rd.sum() > 0 and (ro[:, :, :16] == -1).all(-1).any()
+    for e in envs:
+        e.close()
