@@ -301,3 +301,25 @@ def test_clamped_additions_compose_like_the_window_kernel_assumes():
             r0 = int(rng.choice([-10, -5, 0, 5, 10]))
             incs = [int(v) for v in rng.choice([-5, 0, 5], size=T)]
             assert serial(r0, incs) == prefix(r0, incs)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm: the float64 restatement on the host cores) runs without a GPU and prints ONE
+    JSON line with the keys the driver reads (metric / unit / value, impl, cpu_baseline, e2e with zero copy bytes)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SHIPSIM_BENCH_REF_BUDGET_S="0.5")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "env-steps/sec" and d["unit"] == "env-steps/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["n_gpus"] == 1 and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and d["config"]["envs_per_gpu"] == 4096
