@@ -152,7 +152,9 @@ __global__ void SHIPSIM_WIN_BOUNDS window_kernel(const __grid_constant__ StepPar
         const int nvalid = valid ? min(T, p.K - k0) : 0;        // steps this env still has, capped by the window
         if (__ballot_sync(kFull, nvalid > 0) == 0u) break;
         const bool active = t < nvalid;
-        if (p.auto_reset) {
+        // (Pays only for the longest window, where an SM holds few envs and a reset's loads are fully exposed: at 2,048 envs
+        // +6 %; with T <= 16 the twelve prefetches and their addresses cost more than they hide: -1.2 % on the headline.)
+        if (T >= 32 && p.auto_reset) {
 #pragma unroll
             for (int i = 0; i < (3 + kScr4 + T - 1) / T; ++i) {
                 const int q = t + i * T;
@@ -602,8 +604,8 @@ SHIPSIM_UNROLL(SHIPSIM_SCAN_UNROLL)
                 const int kk = k0 + T + t;
                 a_nx = (valid && kk < p.K) ? load_action(p, act0 + (size_t)kk * act_stride, kk, gid) : 3;
             }
-            // two windows ahead: pull the action rows into L2
-            if (p.action_dtype != 3 && valid && k0 + 2 * T + t < p.K) prefetch_l2(act0 + (size_t)(k0 + 2 * T + t) * act_stride);
+            // two windows ahead: pull the action rows into L2 (longest window only: -1.2 % on the headline with T = 16)
+            if (T >= 32 && p.action_dtype != 3 && valid && k0 + 2 * T + t < p.K) prefetch_l2(act0 + (size_t)(k0 + 2 * T + t) * act_stride);
         }
         __syncwarp();
     }
