@@ -35,8 +35,11 @@
 
 namespace shipsim {
 
+// The two physics scans are unrolled over the whole window when it is short (every shuffle that feeds the chains is then
+// issued ahead of them: 4 -> 16 iterations per trip took the headline from 0.458 to 0.449 ms), by 4 for the longest
+// window (T = 32 fully unrolled is 9 % SLOWER at 2,048 envs: code size).
 #ifndef SHIPSIM_SCAN_UNROLL
-#define SHIPSIM_SCAN_UNROLL T       /* the whole window: the shuffles that feed the chains are all issued ahead of them (4 -> T: 0.458 -> 0.449 ms on the headline) */
+#define SHIPSIM_SCAN_UNROLL (T <= 16 ? T : 4)
 #endif
 #define SHIPSIM_PRAGMA_(x) _Pragma(#x)
 #define SHIPSIM_UNROLL(n) SHIPSIM_PRAGMA_(unroll n)
@@ -413,6 +416,25 @@ SHIPSIM_UNROLL(SHIPSIM_SCAN_UNROLL)
         const int ncommit = do_reset ? __ffs(dmask) - gbase : nvalid;
         const bool commit = t < ncommit;
 
+        // The actions of the next window, now: after a window that commits n steps they are n lanes further along the
+        // (a_my, a_nx) pair, and the lanes at the far end load theirs.  Done here, as soon as n is known, and not at the end
+        // of the iteration: the compiler waits for every outstanding load at the loop's back edge, so a load issued there
+        // was paid in full at the top of every window (4.5 % of the stall samples, ncu); from here it has the ray pass, the
+        // frame and the copy-out to land behind.
+        {
+            const int sh = t + ncommit;                             // (ncommit <= T)
+            const int m1 = __shfl_sync(kFull, a_my, sh, T), m2 = __shfl_sync(kFull, a_nx, sh, T);    // lane (sh mod T) of the group
+            a_my = sh < T ? m1 : m2;
+            a_nx = m2;
+            if (sh >= T) {
+                const int kk = k0 + ncommit + T + t;
+                a_nx = (valid && kk < p.K) ? load_action(p, act0 + (size_t)kk * act_stride, kk, gid) : 3;
+            }
+            // two windows ahead: pull the action rows into L2 (longest window only: -1.2 % on the headline with T = 16)
+            if (T >= 32 && p.action_dtype != 3 && valid && k0 + ncommit + 2 * T + t < p.K) prefetch_l2(act0 + (size_t)(k0 + ncommit + 2 * T + t) * act_stride);
+        }
+
+
         // ---- LiDAR.query (models.py:39-76) of step t at its PRE-integration pose = the pose of step t-1 (ring slot
         // cb + t; the carry for t = 0), for the steps that are committed.  Up to three needy steps per pass, lanes 0-9 /
         // 10-19 / 20-29 = their rays.
@@ -594,18 +616,6 @@ SHIPSIM_UNROLL(SHIPSIM_SCAN_UNROLL)
             cb = ncb;
             r = rn; c0 = c0n; s0 = s0n;
             k0 += ncommit;
-        }
-        {
-            const int sh = t + ncommit;                             // k0 has moved by ncommit (< = T)
-            const int m1 = __shfl_sync(kFull, a_my, sh, T), m2 = __shfl_sync(kFull, a_nx, sh, T);    // lane (sh mod T) of the group
-            a_my = sh < T ? m1 : m2;
-            a_nx = m2;
-            if (sh >= T) {
-                const int kk = k0 + T + t;
-                a_nx = (valid && kk < p.K) ? load_action(p, act0 + (size_t)kk * act_stride, kk, gid) : 3;
-            }
-            // two windows ahead: pull the action rows into L2 (longest window only: -1.2 % on the headline with T = 16)
-            if (T >= 32 && p.action_dtype != 3 && valid && k0 + 2 * T + t < p.K) prefetch_l2(act0 + (size_t)(k0 + 2 * T + t) * act_stride);
         }
         __syncwarp();
     }
