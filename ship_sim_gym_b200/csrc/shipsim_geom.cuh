@@ -5,15 +5,20 @@
 #pragma once
 #include "shipsim_device.cuh"
 
+// how action words are loaded: read once, never again by this SM (streaming: they do not displace the reach-grid and plane records in L1)
+#ifndef SHIPSIM_ACT_LD
+#define SHIPSIM_ACT_LD __ldcs
+#endif
+
 namespace shipsim {
 
 // actions[k][e]: `ap` walks down this env's column (stride = one row of the action tensor, in bytes)
 __device__ __forceinline__ int load_action(const StepParams &p, const char *ap, int k, long long gid)
 {
     switch (p.action_dtype) {
-        case 0: return __ldg(reinterpret_cast<const int *>(ap));
-        case 1: return (int)__ldg(reinterpret_cast<const long long *>(ap));
-        case 2: return (int)__ldg(reinterpret_cast<const unsigned char *>(ap));
+        case 0: return SHIPSIM_ACT_LD(reinterpret_cast<const int *>(ap));
+        case 1: return (int)SHIPSIM_ACT_LD(reinterpret_cast<const long long *>(ap));
+        case 2: return (int)SHIPSIM_ACT_LD(reinterpret_cast<const unsigned char *>(ap));
         default: return random_action(p, gid, p.step0 + (unsigned)k);
     }
 }
@@ -22,9 +27,9 @@ __device__ __forceinline__ int load_action(const StepParams &p, const char *ap, 
 __device__ __forceinline__ int load_action_at(const StepParams &p, size_t idx, int k, long long gid)
 {
     switch (p.action_dtype) {
-        case 0: return __ldg(reinterpret_cast<const int *>(p.actions) + idx);
-        case 1: return (int)__ldg(reinterpret_cast<const long long *>(p.actions) + idx);
-        case 2: return (int)__ldg(reinterpret_cast<const unsigned char *>(p.actions) + idx);
+        case 0: return SHIPSIM_ACT_LD(reinterpret_cast<const int *>(p.actions) + idx);
+        case 1: return (int)SHIPSIM_ACT_LD(reinterpret_cast<const long long *>(p.actions) + idx);
+        case 2: return (int)SHIPSIM_ACT_LD(reinterpret_cast<const unsigned char *>(p.actions) + idx);
         default: return random_action(p, gid, p.step0 + (unsigned)k);
     }
 }
