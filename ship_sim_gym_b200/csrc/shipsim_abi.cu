@@ -132,6 +132,8 @@ struct shipsim_handle {
         cudaStream_t stream = nullptr;
         cudaEvent_t period_begin = nullptr, gen_done = nullptr;
     } fresh;
+    const void *zc_host[4] = {nullptr, nullptr, nullptr, nullptr};     // the last tiny call's buffers and their device aliases
+    void *zc_dev[4] = {nullptr, nullptr, nullptr, nullptr};
     HostPool *pool = nullptr;
     int64_t last_h2d = 0, last_d2h = 0;      // bytes the last shipsim_step_host moved over PCIe
     int64_t launches = 0;
@@ -744,6 +746,39 @@ extern "C" int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int3
     // (Small calls -- a gym-style caller stepping a handful of envs one step at a time -- are latency bound: for them the
     // kernel writes complete rows and everything, copies included, goes through the caller's stream with one wait.)
     const bool small = n < ((size_t)1 << 16);
+    // Tiny calls with page-locked buffers (the gym facade: one env, one step): no copies at all -- the kernel reads the
+    // actions from the caller's memory and writes rows, rewards and done flags straight into it (mapped pinned memory;
+    // a few hundred bytes over PCIe), one launch and one wait.
+    if (n * kFrame * h->cfg.history * sizeof(float) <= ((size_t)1 << 16) && host_obs && host_reward && host_done) {
+        auto mapped = [&](const void *ptr, void **dev) {
+            cudaPointerAttributes attr{};
+            const bool ok = cudaPointerGetAttributes(&attr, ptr) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer;
+            cudaGetLastError();
+            if (ok) *dev = attr.devicePointer;
+            return ok;
+        };
+        void *da = nullptr, *dobs = nullptr, *dr = nullptr, *dd = nullptr;
+        bool all = false;
+        if (h->zc_host[0] == host_actions && h->zc_host[1] == host_obs && h->zc_host[2] == host_reward && h->zc_host[3] == host_done) {
+            da = h->zc_dev[0]; dobs = h->zc_dev[1]; dr = h->zc_dev[2]; dd = h->zc_dev[3];
+            all = da != nullptr;
+        } else if (mapped(host_actions, &da) && mapped(host_obs, &dobs) && mapped(host_reward, &dr) && mapped(host_done, &dd)) {
+            h->zc_host[0] = host_actions; h->zc_host[1] = host_obs; h->zc_host[2] = host_reward; h->zc_host[3] = host_done;
+            h->zc_dev[0] = da; h->zc_dev[1] = dobs; h->zc_dev[2] = dr; h->zc_dev[3] = dd;
+            all = true;
+        } else {
+            h->zc_host[0] = host_actions; h->zc_host[1] = host_obs; h->zc_host[2] = host_reward; h->zc_host[3] = host_done;
+            h->zc_dev[0] = h->zc_dev[1] = h->zc_dev[2] = h->zc_dev[3] = nullptr;                 // (remembered as not mapped)
+        }
+        if (all) {
+            const int rc2 = step_impl(h, da, SHIPSIM_ACTION_I32, K, (float *)dobs, (float *)dr, (uint8_t *)dd, stream, h->cfg.history);
+            if (rc2) return rc2;
+            h->last_h2d = (int64_t)(n * sizeof(int32_t));
+            h->last_d2h = (int64_t)(n * (kFrame * h->cfg.history * sizeof(float) + 5));
+            CU(cudaStreamSynchronize((cudaStream_t)stream));
+            return SHIPSIM_OK;
+        }
+    }
     const bool frames_only = h->cfg.history == 2 && host_obs != nullptr && !small;
     int nd = 0;                                                      // envs [0, nd) by DMA (frames_only)
     bool adaptive = false;
