@@ -218,6 +218,12 @@ int shipsim_mlp_policy_forward(const float *dev_obs, int32_t num_envs, const flo
                                const float *dev_b2, const float *dev_w3, const float *dev_b3, const float *dev_noise, float *dev_out,
                                int64_t *dev_actions, void *stream);
 
+/* Generalised advantage estimation over a finished rollout, as the PPO2 runner the reference trains with computes it
+ * (train/stable_baselines/ppo.py:88,104): dev_rewards[T][N], dev_values[T + 1][N] (the last row = V of the observation after
+ * the rollout), dev_dones[T][N] -> dev_adv[T][N], dev_returns[T][N] = adv + V.  One launch, enqueued on `stream`. */
+int shipsim_gae(const float *dev_rewards, const float *dev_values, const uint8_t *dev_dones, int32_t n_steps, int32_t num_envs, float gamma,
+                float lam, float *dev_adv, float *dev_returns, void *stream);
+
 /* Reduce the per-CTA statistic slots into dev_out[SHIPSIM_STATS_LEN] doubles (device memory, e.g. the tensor
  * handed to ncclAllReduce); clear != 0 zeroes the slots afterwards.  Replaces the counters ShipEnv keeps on the
  * Python object (ship_env.py:150,152,177). */

@@ -1086,6 +1086,15 @@ extern "C" int shipsim_mlp_policy_forward(const float *dev_obs, int32_t num_envs
     return SHIPSIM_OK;
 }
 
+extern "C" int shipsim_gae(const float *dev_rewards, const float *dev_values, const uint8_t *dev_dones, int32_t n_steps, int32_t num_envs, float gamma,
+                           float lam, float *dev_adv, float *dev_returns, void *stream)
+{
+    if (!dev_rewards || !dev_values || !dev_dones || !dev_adv || !dev_returns || n_steps < 1 || num_envs < 1)
+        return fail(SHIPSIM_ERR_ARG, "NULL buffer or bad sizes");
+    CU(launch_gae(dev_rewards, dev_values, dev_dones, n_steps, num_envs, gamma, lam, dev_adv, dev_returns, (cudaStream_t)stream));
+    return SHIPSIM_OK;
+}
+
 extern "C" int shipsim_host_traffic(const shipsim_t *h, int64_t *h2d_bytes, int64_t *d2h_bytes)
 {
     if (!h) return fail(SHIPSIM_ERR_ARG, "NULL argument");

@@ -31,6 +31,8 @@ cudaError_t launch_compact_frames(const float4 *frames, const float4 *prev0, con
 cudaError_t launch_history_rows(const float4 *frames, const float4 *prev0, const uint8_t *done, int N, int nd, int kc, int cut, float4 *rows,
                                 cudaStream_t stream);
 cudaError_t launch_frame(const StepParams &p, float4 *out, cudaStream_t stream);
+cudaError_t launch_gae(const float *rew, const float *val, const unsigned char *done, int T, int N, float gamma, float lam, float *adv, float *ret,
+                       cudaStream_t stream);
 cudaError_t launch_mlp_policy(const float *obs, int n, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
                               const float *b3, const float *noise, float *out, long long *actions, cudaStream_t stream);
 cudaError_t launch_render(const StepParams &p, int e, int img_w, int img_h, uint8_t *rgb, cudaStream_t stream);

@@ -157,6 +157,35 @@ __global__ void __launch_bounds__(64 * kPolSlots, 1) mlp_policy_kernel(const flo
     cp_async_wait_all();
 }
 
+// Generalised advantage estimation over a finished rollout, as PPO2's runner computes it (the reference trains with
+// stable-baselines PPO2: train/stable_baselines/ppo.py:88,104): adv[t] = delta[t] + gamma * lam * nonterminal[t] * adv[t + 1],
+// delta[t] = r[t] + gamma * V[t + 1] * nonterminal[t] - V[t], returns = adv + V.  One thread per env walks its T steps
+// backwards (coalesced across envs): one launch instead of ~T + 8 elementwise torch kernels.
+__global__ void __launch_bounds__(256) gae_kernel(const float *__restrict__ rew, const float *__restrict__ val, const unsigned char *__restrict__ done,
+                                                  int T, int N, float gamma, float gl, float *__restrict__ adv, float *__restrict__ ret)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    float last = 0.f, vnext = __ldg(val + (size_t)T * N + e);
+    for (int t = T - 1; t >= 0; --t) {
+        const size_t i = (size_t)t * N + e;
+        const float nt = done[i] ? 0.f : 1.f, v = __ldg(val + i);
+        const float delta = __ldg(rew + i) + gamma * vnext * nt - v;
+        last = delta + gl * nt * last;
+        adv[i] = last;
+        ret[i] = last + v;
+        vnext = v;
+    }
+}
+
+cudaError_t launch_gae(const float *rew, const float *val, const unsigned char *done, int T, int N, float gamma, float lam, float *adv, float *ret,
+                       cudaStream_t stream)
+{
+    if (T <= 0 || N <= 0) return cudaSuccess;
+    gae_kernel<<<(N + 255) / 256, 256, 0, stream>>>(rew, val, done, T, N, gamma, gamma * lam, adv, ret);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_mlp_policy(const float *obs, int n, const float *w1, const float *b1, const float *w2, const float *b2, const float *w3,
                               const float *b3, const float *noise, float *out, long long *actions, cudaStream_t stream)
 {

@@ -150,7 +150,13 @@ class RolloutCollector(object):
                 env.rollout(self.actions[t:t + 1], out=(self.obs[t + 1:t + 2], self.rewards[t:t + 1], self.dones[t:t + 1]))
             _, v = self.policy(self.obs[T])
             self.values[T].copy_(v)
-        self._gae()
+        if self._kernel:                                # one launch (shipsim_gae) instead of ~T + 8 elementwise kernels
+            from . import _abi
+            with torch.cuda.device(env.device):
+                _abi.check(env.L.shipsim_gae(self.rewards.data_ptr(), self.values.data_ptr(), self.dones.data_ptr(), T, env.num_envs,
+                                             float(self.gamma), float(self.lam), self.adv.data_ptr(), self.returns.data_ptr(), env._stream()))
+        else:
+            self._gae()
 
     def _gae(self):
         """GAE(lambda), as PPO2 computes it: adv[t] = delta[t] + gamma * lam * nonterminal[t] * adv[t + 1], with the deltas

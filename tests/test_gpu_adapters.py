@@ -168,6 +168,21 @@ def test_policy_kernel_matches_the_torch_module(n):
     assert torch.allclose(col.values[1], vv, atol=2e-5, rtol=1e-5)
     lp = torch.log_softmax(lg, -1).gather(-1, col.actions[1][:, None]).squeeze(-1)
     assert torch.allclose(col.logp[1], lp, atol=1e-4)
+    # advantages / returns of the kernel path (shipsim_gae) against the torch formulation of the same recurrence
+    adv_k, ret_k = col.adv.clone(), col.returns.clone()
+    col._gae()
+    assert torch.allclose(adv_k, col.adv, atol=1e-5, rtol=1e-5) and torch.allclose(ret_k, col.returns, atol=1e-5, rtol=1e-5)
+    # ... and with episode ends in the rollout (synthetic: T = 2 is too short for real ones)
+    from ship_sim_gym_b200 import _abi
+    col.dones.copy_((torch.rand(col.dones.shape, device="cuda") < 0.4).to(torch.uint8))
+    col.rewards.normal_()
+    col.values.normal_()
+    _abi.check(env.L.shipsim_gae(col.rewards.data_ptr(), col.values.data_ptr(), col.dones.data_ptr(), col.T, n, float(col.gamma), float(col.lam),
+                                 col.adv.data_ptr(), col.returns.data_ptr(), env._stream()))
+    adv_k, ret_k = col.adv.clone(), col.returns.clone()
+    col._gae()
+    assert col.dones.sum() > 0 or n < 20
+    assert torch.allclose(adv_k, col.adv, atol=1e-5, rtol=1e-5) and torch.allclose(ret_k, col.returns, atol=1e-5, rtol=1e-5)
     env.close()
 
 
