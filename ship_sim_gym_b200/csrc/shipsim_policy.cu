@@ -8,12 +8,13 @@
 // fp32 SIMT, FMA in ascending input order.  No tensor cores: 0.4 GFLOP per step is ~6 us of the FP32 pipes, and the
 // results stay within 1e-5 of the fp32 torch module (bf16 / tf32 operands would not).
 //
-// One CTA per SM, 8 warps = 4 tile slots x 2 trunks; a tile = 32 envs.  The weights (50 KB) are copied into shared memory
+// One CTA per SM, 16 warps = 8 tile slots x 2 trunks; a tile = 16 envs (four warps per scheduler hide the shared-memory
+// latency of the register-tiled products better than two: 18.0 -> 16.4 us at 16,384 envs, -10 % at 65,536).  The weights (50 KB) are copied into shared memory
 // ONCE per CTA by cp.async while the observation tiles are loaded.  (Reading them through L1 cost every 4-input block of
 // the loops an L2 round trip: 40 % of the kernel's cycles were long-scoreboard stalls, ncu; an L1 prefetch did not help.)
-// Each layer is a small SGEMM with an 8 x 8 register tile per thread (8 envs x 8 hidden units: lane = unit group * 4 +
-// env group): per input k a thread reads 8 activations (k-major tile) and 8 weights, two 128-bit shared-memory loads
-// each, conflict-free, and issues 64 FMAs -- 4 FMAs per shared-memory wavefront.  (The very first version gave every
+// Each layer is a small SGEMM with a 4 x 8 register tile per thread (4 envs x 8 hidden units: lane = unit group * 4 +
+// env group): per input k a thread reads 4 activations (k-major tile, one 128-bit load) and 8 weights (two), conflict-free,
+// and issues 32 FMAs.  (The very first version gave every
 // thread one hidden unit and broadcast the activations: a 128-bit broadcast load still costs four wavefronts, and the
 // kernel ran at the shared-memory rate.)
 #include "shipsim_device.cuh"
@@ -24,8 +25,9 @@
 namespace shipsim {
 
 constexpr int kPolD = 32, kPolH = 64, kPolA = 3;      // inputs, hidden units per trunk, actions
-constexpr int kPolE = 32;                             // envs per CTA
-constexpr int kPolT = 8;                              // register tile: kPolT envs x kPolT units per thread
+constexpr int kPolE = 16;                             // envs per tile
+constexpr int kPolT = 8;                              // register tile: kPolM envs x kPolT units per thread
+constexpr int kPolM = kPolE / 4;                      // (4 env groups per warp)
 
 // tanh(x) = 1 - 2 / (exp(2x) + 1) on the special-function unit (ex2.approx + rcp.approx: 7 instructions, |error| < 4e-7,
 // saturates correctly at both ends) instead of libdevice's two-branch tanhf.
@@ -33,22 +35,30 @@ __device__ __forceinline__ float tanh_sfu(float x) { return 1.f - __fdividef(2.f
 
 // acc[m][n] += sum_k act[k][e0 + m] * w[k * ldw + n], k < K: act = k-major shared-memory tile (row = kPolE floats), w = shared memory
 template <int K>
-__device__ __forceinline__ void tile_gemm(float (&acc)[kPolT][kPolT], const float *act, const float *w, int ldw)
+__device__ __forceinline__ void tile_gemm(float (&acc)[kPolM][kPolT], const float *act, const float *w, int ldw)
 {
+    static_assert(kPolM == 4 || kPolM == 8, "one or two 128-bit activation loads per input");
 #pragma unroll 4
     for (int k = 0; k < K; ++k) {
-        const float4 xa = *reinterpret_cast<const float4 *>(act + k * kPolE), xb = *reinterpret_cast<const float4 *>(act + k * kPolE + 4);
+        float x[kPolM];
+        {
+            const float4 xa = *reinterpret_cast<const float4 *>(act + k * kPolE);
+            x[0] = xa.x; x[1] = xa.y; x[2] = xa.z; x[3] = xa.w;
+            if (kPolM == 8) {
+                const float4 xb = *reinterpret_cast<const float4 *>(act + k * kPolE + 4);
+                x[kPolM - 4] = xb.x; x[kPolM - 3] = xb.y; x[kPolM - 2] = xb.z; x[kPolM - 1] = xb.w;
+            }
+        }
         const float4 ca = *reinterpret_cast<const float4 *>(w + k * ldw), cb = *reinterpret_cast<const float4 *>(w + k * ldw + 4);
-        const float x[kPolT] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
         const float c[kPolT] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
 #pragma unroll
-        for (int m = 0; m < kPolT; ++m)
+        for (int m = 0; m < kPolM; ++m)
 #pragma unroll
             for (int n = 0; n < kPolT; ++n) acc[m][n] = fmaf(x[m], c[n], acc[m][n]);
     }
 }
 
-constexpr int kPolSlots = 4;                                          // tiles a CTA works on at once
+constexpr int kPolSlots = 8;                                          // tiles a CTA works on at once
 // the two warps of a slot meet at the slot's own named barrier: slots do not wait for each other (CTA-wide barriers were
 // 20 % of the kernel's stall cycles, ncu: four slots at different points of their tiles, a slot without a tile idling)
 __device__ __forceinline__ void slot_sync(int slot) { asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory"); }
@@ -98,40 +108,41 @@ __global__ void __launch_bounds__(64 * kPolSlots, 1) mlp_policy_kernel(const flo
             __syncthreads();
         } else if (live) slot_sync(slot);                               // later passes: the slot's tile is complete
         if (!live) continue;                                            // (a slot without a tile in this pass has none in any later one)
-        float acc[kPolT][kPolT];
+        float acc[kPolM][kPolT];
         auto init = [&](const float *bias) {
             const float4 ba = __ldg(reinterpret_cast<const float4 *>(bias + u0)), bb = __ldg(reinterpret_cast<const float4 *>(bias + u0) + 1);
             const float b[kPolT] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-            for (int m = 0; m < kPolT; ++m)
+            for (int m = 0; m < kPolM; ++m)
 #pragma unroll
                 for (int nn = 0; nn < kPolT; ++nn) acc[m][nn] = b[nn];
         };
-        auto store_tanh = [&](float *dst) {                             // dst[unit][env]: 8 consecutive envs per unit = two 128-bit stores
+        auto store_tanh = [&](float *dst) {                             // dst[unit][env]: kPolM consecutive envs per unit, 128-bit stores
 #pragma unroll
             for (int nn = 0; nn < kPolT; ++nn) {
-                float4 *d = reinterpret_cast<float4 *>(dst + (u0 + nn) * kPolE + eg * kPolT);
-                d[0] = make_float4(tanh_sfu(acc[0][nn]), tanh_sfu(acc[1][nn]), tanh_sfu(acc[2][nn]), tanh_sfu(acc[3][nn]));
-                d[1] = make_float4(tanh_sfu(acc[4][nn]), tanh_sfu(acc[5][nn]), tanh_sfu(acc[6][nn]), tanh_sfu(acc[7][nn]));
+                float4 *d = reinterpret_cast<float4 *>(dst + (u0 + nn) * kPolE + eg * kPolM);
+#pragma unroll
+                for (int q = 0; q < kPolM / 4; ++q)
+                    d[q] = make_float4(tanh_sfu(acc[4 * q][nn]), tanh_sfu(acc[4 * q + 1][nn]), tanh_sfu(acc[4 * q + 2][nn]), tanh_sfu(acc[4 * q + 3][nn]));
             }
         };
         {
             // layer 1: h1 = tanh(b1 + x W1)          (w1: [32][128], observation scale folded in)
             init(b1);
-            tile_gemm<kPolD>(acc, s_x + eg * kPolT, s_w1 + u0, 2 * kPolH);
+            tile_gemm<kPolD>(acc, s_x + eg * kPolM, s_w1 + u0, 2 * kPolH);
             store_tanh(s_h1);
             __syncwarp();                                               // layer 2 of a trunk reads only what its own warp wrote
             // layer 2, block diagonal: a trunk's units see only that trunk's 64 activations          (w2: [2][64][64])
             init(b2);
-            tile_gemm<kPolH>(acc, s_h1 + trunk * kPolH * kPolE + eg * kPolT, s_w2 + trunk * kPolH * kPolH + ug * kPolT, kPolH);
+            tile_gemm<kPolH>(acc, s_h1 + trunk * kPolH * kPolE + eg * kPolM, s_w2 + trunk * kPolH * kPolH + ug * kPolT, kPolH);
             store_tanh(s_h2);
         }
         slot_sync(slot);
         {
             // heads: thread (o, e) -- o < 3: logit o from the policy trunk, o = 3: value from the value trunk          (w3: [128][4])
 #pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const int o = trunk + 2 * r, e = lane;
+            for (int r = 0; r < (4 * kPolE) / 64; ++r) {
+                const int e = st % kPolE, o = st / kPolE + (64 / kPolE) * r;
                 const int base = o == kPolA ? kPolH : 0;
                 float a = __ldg(b3 + o);
 #pragma unroll 8
