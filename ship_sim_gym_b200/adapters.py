@@ -18,6 +18,18 @@ import torch
 from .env import BatchedShipEnv
 
 
+def tile_images(images):
+    """n pictures [h, w, c] -> one [rows * h, cols * w, c] picture, row-major, black where the grid has no picture
+    (the layout of stable-baselines' tile_images: a near-square grid)."""
+    imgs = np.stack(list(images))
+    n, h, w, c = imgs.shape
+    rows = int(np.ceil(np.sqrt(n)))
+    cols = int(np.ceil(n / rows))
+    pad = np.zeros((rows * cols - n, h, w, c), dtype=imgs.dtype)
+    grid = np.concatenate([imgs, pad]).reshape(rows, cols, h, w, c).transpose(0, 2, 1, 3, 4)
+    return grid.reshape(rows * h, cols * w, c)
+
+
 class ShipVecEnv(object):
     """stable-baselines `VecEnv` over a BatchedShipEnv (auto-reset on, like a SubprocVecEnv worker)."""
 
@@ -65,11 +77,19 @@ class ShipVecEnv(object):
         self.batch.close()
 
     # the rest of the VecEnv surface stable-baselines touches
-    def get_images(self):
-        raise NotImplementedError("rendering is out of scope for the batched env")
+    def get_images(self, max_envs=16, size=(150, 150)):
+        """VecEnv.get_images: one RGB picture per env (uint8 [h, w, 3] numpy arrays), drawn on the device by
+        shipsim_render the way ShipGame.render does (game.py:197-229).  At most `max_envs` pictures of `size` pixels: a
+        batch of thousands is not something to look at."""
+        n = min(self.num_envs, int(max_envs))
+        return [self.batch.render("rgb_array", env_index=i, size=size).cpu().numpy() for i in range(n)]
 
-    def render(self, mode="human"):
-        return None
+    def render(self, mode="human", **kw):
+        """VecEnv.render: the pictures of get_images tiled into one (stable-baselines' tile_images layout: a near-square
+        grid, row-major) for mode 'rgb_array'; 'human' has no window to draw into and returns None."""
+        if mode != "rgb_array":
+            return None
+        return tile_images(self.get_images(**kw))
 
     def seed(self, seed=None):
         return self.batch.seed(seed)

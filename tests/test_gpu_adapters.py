@@ -240,6 +240,16 @@ def test_rgb_array_render_of_one_env():
     x, y = st["pose"][5, :2]
     if 0 < x < 600 and 0 < y < 600:
         assert tuple(img2[min(299, int((600 - y) / 2)), min(299, int(x / 2))]) == (255, 255, 0)
+    # the VecEnv surface: one picture per env, and the tiled overview
+    from ship_sim_gym_b200.adapters import ShipVecEnv
+    venv = ShipVecEnv(num_envs=7, seed=1)
+    venv.reset()
+    pics = venv.get_images(size=(60, 60))
+    assert len(pics) == 7 and pics[0].shape == (60, 60, 3) and pics[0].dtype == np.uint8
+    tiled = venv.render("rgb_array", size=(60, 60))
+    assert tiled.shape == (3 * 60, 3 * 60, 3) and (tiled[:60, 60:120] == pics[1]).all() and (tiled[120:, 60:] == 0).all()
+    assert venv.render() is None
+    venv.close()
     single = ShipEnv(GameConfig, EnvConfig)
     single.reset()
     assert single.render("rgb_array").shape == (600, 600, 3)

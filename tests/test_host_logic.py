@@ -323,3 +323,18 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and d["config"]["envs_per_gpu"] == 4096
+
+
+def test_tile_images_layout():
+    """ShipVecEnv.render('rgb_array') tiles the per-env pictures like stable-baselines' tile_images: near-square grid,
+    row-major, black padding."""
+    pytest.importorskip("torch")
+    from ship_sim_gym_b200.adapters import tile_images
+    imgs = [np.full((4, 6, 3), i + 1, dtype=np.uint8) for i in range(7)]
+    t = tile_images(imgs)
+    assert t.shape == (3 * 4, 3 * 6, 3) and t.dtype == np.uint8
+    for i in range(7):
+        r, c = divmod(i, 3)
+        assert (t[r * 4:(r + 1) * 4, c * 6:(c + 1) * 6] == i + 1).all()
+    assert (t[8:, 6:] == 0).all()
+    assert tile_images(imgs[:1]).shape == (4, 6, 3) and tile_images(imgs[:2]).shape == (8, 6, 3)
