@@ -378,9 +378,12 @@ class BatchedShipEnv(object):
             raise _abi.ShipsimError("call reset() before step()")
         obs, rew, done = out if out is not None else self.alloc_rollout(K)
         code = _abi.ACTION_RANDOM if a is None else _dtype_code(a)
-        with torch.cuda.device(self.device):
-            _abi.check(self.L.shipsim_step(self._h, None if a is None else a.data_ptr(), code, K, obs.data_ptr(),
-                                           rew.data_ptr(), done.data_ptr(), self._stream()))
+        # (no torch.cuda.device() context here: shipsim_step selects the handle's device itself, and on the gym-style K = 1
+        # path the two extra cudaSetDevice calls were a fifth of the per-launch host time)
+        rc = self.L.shipsim_step(self._h, None if a is None else a.data_ptr(), code, K, obs.data_ptr(), rew.data_ptr(), done.data_ptr(),
+                                 torch.cuda.current_stream(self.device).cuda_stream)
+        if rc:
+            _abi.check(rc)
         self.total_steps += K * self.num_envs
         return obs, rew, done
 
