@@ -180,9 +180,13 @@ int shipsim_reset(shipsim_t *h, const uint8_t *dev_mask, const int32_t *dev_scen
 int shipsim_step(shipsim_t *h, const void *dev_actions, int action_dtype, int32_t K, float *dev_obs,
                  float *dev_reward, uint8_t *dev_done, void *stream);
 
-/* Same transition with HOST buffers: copies host_actions up, steps, copies the results back and waits for them
- * (what a CPU-side caller such as the reference's own training scripts sees).  Buffers should be pinned
- * (cudaHostAlloc / torch pin_memory) for the copies to be asynchronous. */
+/* Same transition with HOST buffers: host_actions in, rows / rewards / done flags out, waited for (what a CPU-side caller
+ * such as the reference's own training scripts sees).  Any output pointer may be NULL.  Buffers should be page-locked
+ * (cudaHostAlloc / torch pin_memory); pageable ones work, more slowly.  How the bytes travel depends on the size of the
+ * call: up to 64 KB of rows with page-locked buffers -- no copies, the kernel works on the caller's (mapped) memory; small
+ * calls -- plain copies on `stream`; large ones with HISTORY_SIZE = 2 -- frames compacted on the device (~22 bytes per
+ * env-step over PCIe) and expanded into the rows by `host_threads` host threads, optionally with a share of the envs as
+ * complete rows by DMA.  The results are identical bit for bit in every case. */
 int shipsim_step_host(shipsim_t *h, const int32_t *host_actions, int32_t K, float *host_obs, float *host_reward,
                       uint8_t *host_done, void *stream);
 
