@@ -347,6 +347,7 @@ extern "C" int shipsim_destroy(shipsim_t *h)
     for (auto &ev : h->chunk_done) if (ev) cudaEventDestroy(ev);
     for (auto &ev : h->copy_done) if (ev) cudaEventDestroy(ev);
     if (h->trace0) cudaEventDestroy(h->trace0);
+    for (auto &ev : h->trace_mid) if (ev) cudaEventDestroy(ev);
     if (h->fresh.stream) cudaStreamDestroy(h->fresh.stream);
     if (h->fresh.period_begin) cudaEventDestroy(h->fresh.period_begin);
     if (h->fresh.gen_done) cudaEventDestroy(h->fresh.gen_done);
