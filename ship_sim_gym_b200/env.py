@@ -190,6 +190,7 @@ class BatchedShipEnv(object):
             _abi.check(self.L.shipsim_load_scenarios(self._h, bank.hull_xy.ctypes.data, bank.hull_n.ctypes.data,
                                                      bank.goals.ctypes.data, len(bank), bank.maxv))
         self.params_epoch = getattr(self, "params_epoch", 0) + 1
+        self.graph_safe = True                 # (a host bank leaves fresh-maps mode: shipsim_load_scenarios)
         if getattr(self, "_state_bound", False) and not self._needs_reset:
             self.reset()
 
@@ -208,6 +209,7 @@ class BatchedShipEnv(object):
         self._n_scen = int(n_scenarios)
         self.params_epoch = getattr(self, "params_epoch", 0) + 1
         self._needs_reset = True
+        self.graph_safe = True                 # (a new bank leaves fresh-maps mode: shipsim_generate_scenarios)
 
     def fresh_maps(self, enable=True):
         """A new map for every episode, as ShipGame.reset builds one (game.py:271-272): the device-generated bank
